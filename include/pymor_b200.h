@@ -1,0 +1,153 @@
+/*
+ * pymor_b200.h -- C ABI of libpymor_b200.so: device-resident fp64 snapshot linear algebra for
+ * pyMOR's VectorArray hot path on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  Every entry point replaces one method of the reference's
+ * CPU backend `NumpyVectorArrayImpl` (src/pymor/vectorarrays/numpy.py) or one default method of
+ * `Operator` (src/pymor/operators/interface.py); the file:line it replaces is cited at each
+ * declaration.  The host side (pymor_b200/vectorarray.py, ctypes) binds exactly these symbols.
+ *
+ * Conventions
+ * -----------
+ *  - All data are IEEE fp64.  A *panel* is a set of `k` columns of `n` contiguous doubles each:
+ *    column c starts at `ptr + c*cs` (cs = column stride in doubles; any sign; 0 = broadcast one
+ *    column).  This is the reference's Fortran-ordered (dim, len) ndarray (numpy.py:16-18) with the
+ *    view arithmetic (slice start/step) already folded into `ptr`/`cs` by the caller.
+ *  - Device memory is allocated and owned by the caller (torch); the library only borrows raw
+ *    pointers for the duration of a call.  All work is enqueued on the context's stream.
+ *  - `out*` result pointers must be device-accessible: device memory (multi-GPU partials that are
+ *    all-reduced afterwards) or pinned/mapped host memory (single-GPU: the kernel writes the
+ *    result straight to the host).  With PMC_SYNC the stream is synchronised before returning.
+ *  - Return value: 0 on success, negative pmc_status on failure; pmc_last_error() gives the
+ *    message (thread-local).  No exceptions cross the boundary, no global state besides pmc_ctx.
+ *  - `n` is the LOCAL number of rows (DOFs) of this rank's shard; reductions return local
+ *    partial sums (the reference's MPI backend does the same, vectorarrays/mpi.py:394-416).
+ */
+#ifndef PYMOR_B200_H
+#define PYMOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMC_VERSION 100
+
+typedef enum {
+    PMC_OK = 0,
+    PMC_ERR_INVALID = -1,     /* bad argument */
+    PMC_ERR_CUDA = -2,        /* CUDA runtime/driver error (message in pmc_last_error) */
+    PMC_ERR_WORKSPACE = -3,   /* workspace too small; pmc_ctx_workspace_needed() tells how much */
+    PMC_ERR_UNSUPPORTED = -4
+} pmc_status;
+
+/* flags */
+#define PMC_SYNC 1u        /* synchronise the stream before returning (results visible on host) */
+#define PMC_SYMMETRIC 2u   /* pmc_gram: B is the same panel as A -> SYRK (lower tiles + mirror)  */
+#define PMC_FORCE_SIMPLE 4u /* use the generic DFMA kernel even where the TMA/DMMA path applies (tests) */
+
+typedef struct pmc_ctx pmc_ctx;
+
+int pmc_version(void);
+const char *pmc_last_error(void);
+
+/* Context: one per (device, stream).  `stream` is a cudaStream_t (0 = legacy default stream). */
+int pmc_ctx_create(int device, void *stream, pmc_ctx **out);
+int pmc_ctx_destroy(pmc_ctx *ctx);
+/* Caller-owned scratch (device memory) for split partials; must be 256-byte aligned. */
+int pmc_ctx_set_workspace(pmc_ctx *ctx, void *dev_ptr, size_t bytes);
+size_t pmc_ctx_workspace_needed(pmc_ctx *ctx); /* bytes asked for by the last PMC_ERR_WORKSPACE */
+int pmc_ctx_sync(pmc_ctx *ctx);
+int pmc_ctx_sm_count(pmc_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t pmc_ctx_launch_count(pmc_ctx *ctx);
+
+/* inner / gramian / apply2 with a diagonal product.
+ * out[i + j*ldo] = sum_d A[d + i*csA] * w[d] * B[d + j*csB]   (w == NULL: Euclidean)
+ * Replaces NumpyVectorArrayImpl.inner (vectorarrays/numpy.py:155-163), VectorArrayImpl.gramian
+ * (vectorarrays/interface.py:1068-1069) and Operator.apply2 for a diagonal matrix operator
+ * (operators/interface.py:79-109 with operators/numpy.py:232-237).
+ * Large, TMA-describable panels run on the TMA + FP64 tensor-core (DMMA) kernel; everything else
+ * on the generic kernel.  PMC_SYMMETRIC computes only the lower tile triangle and mirrors, so the
+ * result is bitwise symmetric like the reference's dsyrk path. */
+int pmc_gram(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const double *B, int64_t csB,
+             int32_t kB, int64_t n, const double *w, double *out, int64_t ldo, uint32_t flags);
+
+/* lincomb:  R[d + j*csR] = sum_i A[d + i*csA] * CT[i + j*ldc],  j < m.
+ * CT is DEVICE memory holding the (k x m) coefficient matrix in Fortran order (column j of the
+ * coefficients contiguous), ldc >= k.  Replaces NumpyVectorArrayImpl.lincomb
+ * (vectorarrays/numpy.py:175-180). */
+int pmc_lincomb(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n, const double *CT,
+                int64_t ldc, int32_t m, double *R, int64_t csR, uint32_t flags);
+
+/* pairwise_inner / pairwise_apply2 with a diagonal product:
+ * out[c] = sum_d A[d + c*csA] * w[d] * B[d + c*csB].
+ * Replaces NumpyVectorArrayImpl.pairwise_inner (vectorarrays/numpy.py:165-173) and
+ * Operator.pairwise_apply2 (operators/interface.py:111-143). */
+int pmc_pairwise_inner(pmc_ctx *ctx, const double *A, int64_t csA, const double *B, int64_t csB,
+                       int32_t k, int64_t n, const double *w, double *out, uint32_t flags);
+
+/* norm2: out[c] = sum_d w[d] * A[d + c*csA]^2.  Replaces NumpyVectorArrayImpl.norm2/norm
+ * (vectorarrays/numpy.py:182-194). */
+int pmc_norm2(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n, const double *w,
+              double *out, uint32_t flags);
+
+/* axpy: Y[:, c] += alpha[c or 0] * X[:, c]  (csX == 0 broadcasts one x column).
+ * alpha is a HOST array of n_alpha (1 or k) doubles.  Replaces NumpyVectorArrayImpl.axpy
+ * (vectorarrays/numpy.py:112-138). */
+int pmc_axpy(pmc_ctx *ctx, double *Y, int64_t csY, const double *X, int64_t csX, int32_t k,
+             int64_t n, const double *alpha, int32_t n_alpha, uint32_t flags);
+
+/* scal: Y[:, c] *= alpha[c or 0].  Replaces NumpyVectorArrayImpl.scal (numpy.py:85-100). */
+int pmc_scal(pmc_ctx *ctx, double *Y, int64_t csY, int32_t k, int64_t n, const double *alpha,
+             int32_t n_alpha, uint32_t flags);
+
+/* copy of a strided panel: D[:, c] = S[:, c].  Replaces the slicing copies in
+ * NumpyVectorArrayImpl.copy/append (numpy.py:58-83). */
+int pmc_copy(pmc_ctx *ctx, double *D, int64_t csD, const double *S, int64_t csS, int32_t k,
+             int64_t n, uint32_t flags);
+
+/* gather of arbitrary (possibly repeated) columns: D[:, c] = base[:, idx[c]] with leading dimension
+ * ld; idx is a HOST array.  Replaces fancy indexing `self._array[:, ind]` (numpy.py:21, :59). */
+int pmc_gather_cols(pmc_ctx *ctx, double *D, int64_t csD, const double *base, int64_t ld,
+                    const int64_t *idx, int32_t k, int64_t n, uint32_t flags);
+
+/* dofs: out[i + c*ndofs] = A[dof[i] + c*csA]; dof is a HOST array of local row indices.
+ * Replaces NumpyVectorArrayImpl.dofs (numpy.py:196-201). */
+int pmc_dofs(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n, const int64_t *dof,
+             int32_t ndofs, double *out, uint32_t flags);
+
+/* amax: per column the FIRST row index of maximal |value| and that value.
+ * Replaces NumpyVectorArrayImpl.amax (numpy.py:203-211). */
+int pmc_amax(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n, int64_t *out_idx,
+             double *out_val, uint32_t flags);
+
+/* Y[:, c] = w .* X[:, c]: Operator.apply of a diagonal matrix operator
+ * (operators/numpy.py:232-237 for a scipy dia/csr diagonal matrix). */
+int pmc_diag_apply(pmc_ctx *ctx, const double *w, const double *X, int64_t csX, double *Y,
+                   int64_t csY, int32_t k, int64_t n, uint32_t flags);
+
+/* CSR operator.apply:  Y[r + c*csY] = sum_{p in row r} vals[p] * X[colidx[p] + c*csX].
+ * rowptr (int64, nrows+1), colidx (int32), vals (fp64) are DEVICE arrays.  Replaces
+ * NumpyMatrixOperator.apply for scipy sparse matrices (operators/numpy.py:232-237). */
+int pmc_csr_apply(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
+                  const double *vals, const double *X, int64_t csX, double *Y, int64_t csY,
+                  int32_t k, uint32_t flags);
+
+/* Fused CSR two-form  out[i + j*ldo] = sum_r V[r + i*csV] * (M U)[r, j]  without materialising the
+ * n x k product M U: row panels of M U are formed in the workspace and contracted at once.
+ * Replaces Operator.apply2 = V.inner(op.apply(U)) (operators/interface.py:79-109). */
+int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
+                 const double *vals, const double *V, int64_t csV, int32_t kV, const double *U,
+                 int64_t csU, int32_t kU, double *out, int64_t ldo, uint32_t flags);
+
+/* Roofline denominators measured on the spot: sustained FP64 tensor-core (DMMA) and DFMA
+ * throughput in TFLOP/s over `ms` milliseconds of back-to-back issue on every SM. */
+int pmc_measure_fp64_peak(pmc_ctx *ctx, int use_dmma, double ms, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMOR_B200_H */

@@ -1,0 +1,111 @@
+// CSR operator kernels: Y = M X on column panels, and the fused two-form V^T (M U) that never
+// materialises the n x k product (row panels of M U live in the workspace and are contracted by
+// the Gram kernel while still L2-resident).
+//
+// Algorithmic work: apply: 2*nnz*k flop, 12*nnz + 16*n*k bytes;  two-form: + 2*n*kV*kU flop.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CJ = 8;          // panel columns per thread (matrix entries are read once per CJ columns)
+constexpr int CSR_THREADS = 256;
+
+__global__ void __launch_bounds__(CSR_THREADS)
+csr_apply_kernel(int64_t row0, int64_t nrows, const int64_t *__restrict__ rowptr,
+                 const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+                 const double *__restrict__ X, int64_t csX, double *__restrict__ Y, int64_t csY, int k) {
+    const int64_t r = (int64_t)blockIdx.x * CSR_THREADS + threadIdx.x;
+    if (r >= nrows) return;
+    const int j0 = blockIdx.y * CJ;
+    const int64_t p0 = rowptr[row0 + r], p1 = rowptr[row0 + r + 1];
+    double acc[CJ];
+#pragma unroll
+    for (int jj = 0; jj < CJ; ++jj) acc[jj] = 0.0;
+    if (j0 + CJ <= k) {
+        for (int64_t p = p0; p < p1; ++p) {
+            const double v = vals[p];
+            const double *x = X + colidx[p] + (int64_t)j0 * csX;
+#pragma unroll
+            for (int jj = 0; jj < CJ; ++jj) acc[jj] = fma(v, x[(int64_t)jj * csX], acc[jj]);
+        }
+    } else {
+        for (int64_t p = p0; p < p1; ++p) {
+            const double v = vals[p];
+            const double *x = X + colidx[p] + (int64_t)j0 * csX;
+#pragma unroll
+            for (int jj = 0; jj < CJ; ++jj)
+                if (j0 + jj < k) acc[jj] = fma(v, x[(int64_t)jj * csX], acc[jj]);
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < CJ; ++jj)
+        if (j0 + jj < k) Y[r + (int64_t)(j0 + jj) * csY] = acc[jj];
+}
+
+int launch_csr_apply(pmc_ctx *ctx, int64_t row0, int64_t nrows, const int64_t *rowptr,
+                     const int32_t *colidx, const double *vals, const double *X, int64_t csX, double *Y,
+                     int64_t csY, int k) {
+    dim3 grid((unsigned)ceil_div64(nrows, CSR_THREADS), (k + CJ - 1) / CJ);
+    csr_apply_kernel<<<grid, CSR_THREADS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX, Y,
+                                                          csY, k);
+    ctx->launches += 1;
+    PMC_CHECK_CUDA(cudaGetLastError());
+    return PMC_OK;
+}
+
+}  // namespace
+
+extern "C" int pmc_csr_apply(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
+                             const double *vals, const double *X, int64_t csX, double *Y, int64_t csY,
+                             int32_t k, uint32_t flags) {
+    PMC_REQUIRE(ctx && nrows >= 0 && k >= 0, "bad arguments");
+    if (nrows == 0 || k == 0) return pmc_after_launch(ctx, 0, flags);
+    PMC_REQUIRE(rowptr && colidx && vals && X && Y, "NULL pointer");
+    int rc = launch_csr_apply(ctx, 0, nrows, rowptr, colidx, vals, X, csX, Y, csY, k);
+    if (rc) return rc;
+    return pmc_after_launch(ctx, 0, flags);
+}
+
+extern "C" int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
+                            const double *vals, const double *V, int64_t csV, int32_t kV, const double *U,
+                            int64_t csU, int32_t kU, double *out, int64_t ldo, uint32_t flags) {
+    PMC_REQUIRE(ctx && nrows >= 0 && kV >= 0 && kU >= 0, "bad arguments");
+    if (kV == 0 || kU == 0) return pmc_after_launch(ctx, 0, flags);
+    PMC_REQUIRE(out && ldo >= kV, "bad output");
+    if (nrows == 0) {
+        PMC_CHECK_CUDA(cudaMemset2DAsync(out, ldo * sizeof(double), 0, kV * sizeof(double), kU, ctx->stream));
+        return pmc_after_launch(ctx, 0, flags);
+    }
+    PMC_REQUIRE(rowptr && colidx && vals && V && U, "NULL pointer");
+
+    // Workspace layout: [ T panel (PR x kU, leading dimension PR) | Gram split partials ].
+    // The T panel is kept <= 48 MB so that it is still in the 126 MB L2 when the Gram kernel reads it.
+    const size_t panel_budget = (size_t)48 << 20;
+    int64_t PR = (int64_t)(panel_budget / ((size_t)kU * 8));
+    PR = (PR / 128) * 128;
+    if (PR < 2048) PR = 2048;
+    if (PR > nrows) PR = round_up64(nrows, 16);
+    const size_t panel_bytes = (size_t)PR * kU * 8;
+    const size_t panel_region = (panel_bytes + 255) & ~(size_t)255;
+    if (ctx->ws == nullptr || ctx->ws_bytes < panel_region + ((size_t)64 << 20)) {
+        ctx->ws_needed = panel_region + ((size_t)512 << 20);
+        pmc_set_error("workspace too small: need %zu bytes, have %zu", ctx->ws_needed, ctx->ws_bytes);
+        return PMC_ERR_WORKSPACE;
+    }
+    double *T = static_cast<double *>(ctx->ws);
+    void *gws = static_cast<char *>(ctx->ws) + panel_region;
+    const size_t gws_cap = ctx->ws_bytes - panel_region;
+    const uint32_t gflags = flags & PMC_FORCE_SIMPLE;
+
+    int first = 1;
+    for (int64_t r0 = 0; r0 < nrows; r0 += PR) {
+        const int64_t pr = (nrows - r0 < PR) ? nrows - r0 : PR;
+        int rc = launch_csr_apply(ctx, r0, pr, rowptr, colidx, vals, U, csU, T, PR, kU);
+        if (rc) return rc;
+        rc = pmc_gram_impl(ctx, V + r0, csV, kV, T, PR, kU, pr, nullptr, out, ldo, gflags, gws, gws_cap,
+                           first ? 0 : 1);
+        if (rc) return rc;
+        first = 0;
+    }
+    return pmc_after_launch(ctx, 0, flags);
+}

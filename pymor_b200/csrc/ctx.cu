@@ -1,0 +1,113 @@
+// Context, error reporting and TMA descriptor encoding for libpymor_b200.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void pmc_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int pmc_version(void) { return PMC_VERSION; }
+extern "C" const char *pmc_last_error(void) { return g_err; }
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
+    PMC_REQUIRE(out != nullptr, "out is NULL");
+    int ndev = 0;
+    PMC_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    PMC_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+    PMC_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PMC_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        pmc_set_error("libpymor_b200 is built for sm_100a only; device %d is sm_%d%d", device,
+                      prop.major, prop.minor);
+        return PMC_ERR_UNSUPPORTED;
+    }
+    pmc_ctx *c = new pmc_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+    c->sm_count = prop.multiProcessorCount;
+    c->n_tickets = 4096;
+    c->partials_cap = 1 << 16;
+    if (cudaMalloc(&c->tickets, c->n_tickets * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(c->tickets, 0, c->n_tickets * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&c->partials, (size_t)c->partials_cap * 16) != cudaSuccess) {
+        pmc_set_error("cannot allocate ticket counters / block partials");
+        delete c;
+        return PMC_ERR_CUDA;
+    }
+    cudaDriverEntryPointQueryResult q;
+    void *fn = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) {
+        pmc_set_error("cuTensorMapEncodeTiled not available from the driver");
+        cudaFree(c->tickets);
+        cudaFree(c->partials);
+        delete c;
+        return PMC_ERR_CUDA;
+    }
+    c->encode_tiled = fn;
+    *out = c;
+    return PMC_OK;
+}
+
+extern "C" int pmc_ctx_destroy(pmc_ctx *ctx) {
+    if (!ctx) return PMC_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->tickets);
+    cudaFree(ctx->partials);
+    delete ctx;
+    return PMC_OK;
+}
+
+extern "C" int pmc_ctx_set_workspace(pmc_ctx *ctx, void *dev_ptr, size_t bytes) {
+    PMC_REQUIRE(ctx != nullptr, "ctx is NULL");
+    PMC_REQUIRE((reinterpret_cast<uintptr_t>(dev_ptr) & 255) == 0, "workspace must be 256B aligned");
+    ctx->ws = dev_ptr;
+    ctx->ws_bytes = bytes;
+    return PMC_OK;
+}
+
+extern "C" size_t pmc_ctx_workspace_needed(pmc_ctx *ctx) { return ctx ? ctx->ws_needed : 0; }
+
+extern "C" int pmc_ctx_sync(pmc_ctx *ctx) {
+    PMC_REQUIRE(ctx != nullptr, "ctx is NULL");
+    PMC_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PMC_OK;
+}
+
+extern "C" int pmc_ctx_sm_count(pmc_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int64_t pmc_ctx_launch_count(pmc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pmc_encode_tmap_f64(pmc_ctx *ctx, CUtensorMap *tm, const void *base, int rank, uint64_t dim0,
+                        uint64_t dim1, uint64_t stride1_bytes, uint32_t box0, uint32_t box1,
+                        bool swizzle128) {
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstr[1] = {stride1_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    encode_tiled_fn fn = reinterpret_cast<encode_tiled_fn>(ctx->encode_tiled);
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void *>(base),
+                    gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pmc_set_error("cuTensorMapEncodeTiled failed (CUresult %d): base=%p rank=%d dims=(%llu,%llu) "
+                      "stride=%llu box=(%u,%u)",
+                      (int)r, base, rank, (unsigned long long)dim0, (unsigned long long)dim1,
+                      (unsigned long long)stride1_bytes, box0, box1);
+        return PMC_ERR_CUDA;
+    }
+    return PMC_OK;
+}

@@ -1,0 +1,337 @@
+// Tall-skinny Gram / SYRK  G = A^T diag(w) B  for column panels with n >> k.
+//
+//   gram_dmma_kernel : TMA (128B-swizzled [128 cols x 16 rows] boxes) -> 6-stage mbarrier ring ->
+//                      FP64 tensor-core MMA (mma.sync m8n8k4.f64, SASS DMMA.8x8x4), 128x128 output
+//                      tile per CTA held in registers, rows split across CTAs (split-n).
+//   gram_simple_kernel: generic DFMA kernel for panels TMA cannot describe (odd / negative /
+//                      zero column stride, misaligned base) and for tiny operands.
+//   gram_reduce_kernel: fixed-order sum of the split partials, mirror for SYRK, write to `out`
+//                      (device or mapped host memory).  Fixed order => bitwise reproducible.
+//
+// Algorithmic work: 2*n*kA*kB flop (n*k*(k+1) for SYRK), 8*n*(kA+kB) bytes (8*n*k for SYRK).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// DMMA kernel
+// ------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 6;
+constexpr int GRAM_THREADS = 512;                 // 16 warps, 4 (M) x 4 (N), warp tile 32x32
+constexpr int TILE_ELEMS = BM * BK;               // 2048 doubles = 16 KB
+constexpr uint32_t TILE_BYTES = TILE_ELEMS * 8;
+constexpr size_t GRAM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * (2 * TILE_BYTES + BK * 8) +
+                             2 * STAGES * sizeof(uint64_t) + 64;
+
+struct GramParams {
+    int64_t n;
+    int64_t rows_per_split;   // multiple of BK
+    int tiles_m, tiles_n, ntiles;
+    int symmetric;
+    double *partials;         // [item][BN][BM]
+};
+
+__device__ __forceinline__ void decode_tile(const GramParams &p, int tile, int &ti, int &tj) {
+    if (p.symmetric) {
+        int rem = tile;
+        tj = 0;
+        while (rem >= p.tiles_m - tj) { rem -= p.tiles_m - tj; ++tj; }
+        ti = tj + rem;
+    } else {
+        ti = tile % p.tiles_m;
+        tj = tile / p.tiles_m;
+    }
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmW, const GramParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // 1024B alignment: the 128B swizzle pattern is a function of the absolute smem address
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    double *sA = reinterpret_cast<double *>(smem);
+    double *sB = sA + STAGES * TILE_ELEMS;
+    double *sW = sB + STAGES * TILE_ELEMS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sW + STAGES * BK);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t = lane & 3;
+
+    const int item = blockIdx.x;
+    const int tile = item % p.ntiles, split = item / p.ntiles;
+    int ti, tj;
+    decode_tile(p, tile, ti, tj);
+    const bool diag = p.symmetric && ti == tj;
+    const int64_t r0 = (int64_t)split * p.rows_per_split;
+    const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
+    const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (WEIGHTED) tma_prefetch_desc(&tmW);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], GRAM_THREADS / 32);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const uint32_t stage_bytes = TILE_BYTES * (diag ? 1u : 2u) + (WEIGHTED ? BK * 8u : 0u);
+    auto issue = [&](int kt) {
+        const int s = kt % STAGES;
+        const int32_t d = (int32_t)(r0 + (int64_t)kt * BK);
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        tma_load_2d(sA + s * TILE_ELEMS, &tmA, &full[s], d, ti * BM);
+        if (!diag) tma_load_2d(sB + s * TILE_ELEMS, &tmB, &full[s], d, tj * BN);
+        if (WEIGHTED) tma_load_1d(sW + s * BK, &tmW, &full[s], d);
+    };
+    if (tid == 0) {
+        const int pre = nk < STAGES ? nk : STAGES;
+        for (int kt = 0; kt < pre; ++kt) issue(kt);
+    }
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    // per-thread swizzled offsets (in doubles) inside a 128-byte row, one per k-step of 4
+    const int q = g ^ ((lane >> 1) & 1);
+    int swz[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) swz[ks] = ((((ks * 2) ^ q) << 1) + (lane & 1));
+    const int rowA = (wm * 32 + g) * BK;
+    const int rowB = (wn * 32 + g) * BK;
+
+    for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % STAGES;
+        // producer: refill the stage everybody released one iteration ago
+        if (tid == 0 && kt >= 1 && kt - 1 + STAGES < nk) {
+            const int sp = (kt - 1) % STAGES;
+            mbar_wait(&empty[sp], ((kt - 1) / STAGES) & 1);
+            issue(kt - 1 + STAGES);
+        }
+        mbar_wait(&full[s], (kt / STAGES) & 1);
+        const double *a_s = sA + s * TILE_ELEMS + rowA;
+        const double *b_s = (diag ? sA : sB) + s * TILE_ELEMS + rowB;
+        const double *w_s = sW + s * BK + t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * BK + swz[ks]];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = b_s[ni * 8 * BK + swz[ks]];
+            if (WEIGHTED) {
+                const double wv = w_s[ks * 4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] *= wv;
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // epilogue: partial tile, column-major [j][i]
+    double *out = p.partials + (size_t)item * (BM * BN);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int i = wm * 32 + mi * 8 + g;
+            const int j = wn * 32 + ni * 8 + 2 * t;
+            out[(size_t)j * BM + i] = acc[mi][ni][0];
+            out[(size_t)(j + 1) * BM + i] = acc[mi][ni][1];
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic kernel: 32x32 output tile, 256 threads (2x2 outputs each), 64 rows per step
+// ------------------------------------------------------------------------------------------
+constexpr int SM_T = 32, SM_K = 64, SM_PITCH = SM_K + 1, SM_THREADS = 256;
+
+__global__ void __launch_bounds__(SM_THREADS)
+gram_simple_kernel(const double *__restrict__ A, int64_t csA, int kA, const double *__restrict__ B,
+                   int64_t csB, int kB, const double *__restrict__ w, const GramParams p) {
+    __shared__ double As[SM_T * SM_PITCH];
+    __shared__ double Bs[SM_T * SM_PITCH];
+    const int tid = threadIdx.x;
+    const int item = blockIdx.x;
+    const int tile = item % p.ntiles, split = item / p.ntiles;
+    int ti, tj;
+    decode_tile(p, tile, ti, tj);
+    const int64_t r0 = (int64_t)split * p.rows_per_split;
+    const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
+    const int tx = tid & 15, ty = tid >> 4;
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+    for (int64_t d0 = r0; d0 < r1; d0 += SM_K) {
+#pragma unroll
+        for (int r = 0; r < (SM_T * SM_K) / SM_THREADS; ++r) {
+            const int e = tid + r * SM_THREADS;
+            const int ci = e / SM_K, dd = e % SM_K;
+            const int64_t d = d0 + dd;
+            const int ca = ti * SM_T + ci, cb = tj * SM_T + ci;
+            double av = 0.0, bv = 0.0;
+            if (d < r1) {
+                if (ca < kA) av = A[(int64_t)ca * csA + d];
+                if (cb < kB) {
+                    bv = B[(int64_t)cb * csB + d];
+                    if (w) bv *= w[d];
+                }
+            }
+            As[ci * SM_PITCH + dd] = av;
+            Bs[ci * SM_PITCH + dd] = bv;
+        }
+        __syncthreads();
+        const double *a0 = As + (ty * 2) * SM_PITCH, *a1 = a0 + SM_PITCH;
+        const double *b0 = Bs + (tx * 2) * SM_PITCH, *b1 = b0 + SM_PITCH;
+#pragma unroll 16
+        for (int dd = 0; dd < SM_K; ++dd) {
+            const double x0 = a0[dd], x1 = a1[dd], y0 = b0[dd], y1 = b1[dd];
+            c00 = fma(x0, y0, c00);
+            c01 = fma(x0, y1, c01);
+            c10 = fma(x1, y0, c10);
+            c11 = fma(x1, y1, c11);
+        }
+        __syncthreads();
+    }
+    double *out = p.partials + (size_t)item * (SM_T * SM_T);
+    const int i = ty * 2, j = tx * 2;
+    out[j * SM_T + i] = c00;
+    out[(j + 1) * SM_T + i] = c01;
+    out[j * SM_T + i + 1] = c10;
+    out[(j + 1) * SM_T + i + 1] = c11;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 2: out[i + j*ldo] = sum_split partial[split][tile][j][i]   (+ mirror for SYRK)
+// ------------------------------------------------------------------------------------------
+__global__ void gram_reduce_kernel(const double *__restrict__ partials, int T, int nsplit,
+                                   GramParams p, int kA, int kB, double *__restrict__ out,
+                                   int64_t ldo, int accumulate) {
+    const int tile = blockIdx.y;
+    int ti, tj;
+    decode_tile(p, tile, ti, tj);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * T) return;
+    const int il = e % T, jl = e / T;
+    const int gi = ti * T + il, gj = tj * T + jl;
+    if (gi >= kA || gj >= kB) return;
+    if (p.symmetric && ti == tj && gi < gj) return;  // strictly-upper part of diagonal tiles: mirrored
+    const size_t tile_elems = (size_t)T * T;
+    const double *src = partials + (size_t)tile * tile_elems + e;
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += src[(size_t)sp * p.ntiles * tile_elems];
+    if (accumulate) s += out[gi + (int64_t)gj * ldo];
+    out[gi + (int64_t)gj * ldo] = s;
+    if (p.symmetric && gi != gj) out[gj + (int64_t)gi * ldo] = s;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const double *B,
+                  int64_t csB, int32_t kB, int64_t n, const double *w, double *out, int64_t ldo,
+                  uint32_t flags, void *ws, size_t ws_cap, int accumulate) {
+    PMC_REQUIRE(ctx && kA >= 0 && kB >= 0 && n >= 0, "bad arguments");
+    if (kA == 0 || kB == 0) return pmc_after_launch(ctx, 0, flags);
+    PMC_REQUIRE(out != nullptr && ldo >= kA, "bad output");
+    const bool sym = (flags & PMC_SYMMETRIC) != 0;
+    if (sym) PMC_REQUIRE(A == B && csA == csB && kA == kB, "PMC_SYMMETRIC needs identical panels");
+    if (n == 0) {
+        if (!accumulate)
+            PMC_CHECK_CUDA(cudaMemset2DAsync(out, ldo * sizeof(double), 0, kA * sizeof(double), kB, ctx->stream));
+        return pmc_after_launch(ctx, 0, flags);
+    }
+    PMC_REQUIRE(A && B, "NULL panel");
+
+    const bool tma_ok = !(flags & PMC_FORCE_SIMPLE) && csA > 0 && csB > 0 && (csA % 2) == 0 &&
+                        (csB % 2) == 0 && aligned16(A) && aligned16(B) && (!w || aligned16(w)) &&
+                        n >= BK && n < (int64_t)1 << 31 && csA < ((int64_t)1 << 36) &&
+                        csB < ((int64_t)1 << 36) && (kA >= 16 || kB >= 16);
+    const int T = tma_ok ? BM : SM_T;
+    const int rows_q = tma_ok ? BK : SM_K;
+
+    GramParams p;
+    p.n = n;
+    p.symmetric = sym ? 1 : 0;
+    p.tiles_m = (kA + T - 1) / T;
+    p.tiles_n = (kB + T - 1) / T;
+    p.ntiles = sym ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
+
+    // split-n: aim at ~4 full waves of CTAs (1 CTA/SM for the DMMA kernel), each item >= 64 steps
+    const int64_t steps = ceil_div64(n, rows_q);
+    const int ctas_per_wave = ctx->sm_count * (tma_ok ? 1 : 4);
+    int64_t nsplit = ceil_div64((int64_t)4 * ctas_per_wave, p.ntiles);
+    const int64_t max_split = steps / 64 > 0 ? steps / 64 : 1;
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 1) {
+        // round the item count up to a whole number of waves where that is cheap
+        int64_t items = nsplit * p.ntiles;
+        int64_t waves = ceil_div64(items, ctas_per_wave);
+        int64_t ns2 = (waves * ctas_per_wave) / p.ntiles;
+        if (ns2 >= 1 && ns2 <= max_split) nsplit = ns2;
+    }
+    p.rows_per_split = round_up64(ceil_div64(n, nsplit), rows_q);
+    nsplit = ceil_div64(n, p.rows_per_split);
+    const int64_t items = nsplit * p.ntiles;
+    const size_t ws_bytes = (size_t)items * T * T * sizeof(double);
+    if (ws_bytes > ws_cap || ws == nullptr) {
+        ctx->ws_needed = ws_bytes + ((char *)ws - (char *)ctx->ws);
+        pmc_set_error("workspace too small: need %zu bytes, have %zu", ctx->ws_needed, ctx->ws_bytes);
+        return PMC_ERR_WORKSPACE;
+    }
+    int rc;
+    p.partials = static_cast<double *>(ws);
+
+    if (tma_ok) {
+        CUtensorMap tmA, tmB, tmW;
+        rc = pmc_encode_tmap_f64(ctx, &tmA, A, 2, (uint64_t)n, (uint64_t)kA, (uint64_t)csA * 8, BK, BM, true);
+        if (rc) return rc;
+        rc = pmc_encode_tmap_f64(ctx, &tmB, B, 2, (uint64_t)n, (uint64_t)kB, (uint64_t)csB * 8, BK, BN, true);
+        if (rc) return rc;
+        if (w) {
+            rc = pmc_encode_tmap_f64(ctx, &tmW, w, 1, (uint64_t)n, 1, 0, BK, 1, false);
+            if (rc) return rc;
+        } else {
+            tmW = tmA;
+        }
+        if (w) {
+            PMC_CHECK_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
+            gram_dmma_kernel<true><<<(unsigned)items, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+        } else {
+            PMC_CHECK_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
+            gram_dmma_kernel<false><<<(unsigned)items, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+        }
+    } else {
+        gram_simple_kernel<<<(unsigned)items, SM_THREADS, 0, ctx->stream>>>(A, csA, kA, B, csB, kB, w, p);
+    }
+    PMC_CHECK_CUDA(cudaGetLastError());
+    dim3 rgrid((T * T + 255) / 256, p.ntiles);
+    gram_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(p.partials, T, (int)nsplit, p, kA, kB, out, ldo,
+                                                       accumulate);
+    return pmc_after_launch(ctx, 2, flags);
+}
+
+extern "C" int pmc_gram(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const double *B,
+                        int64_t csB, int32_t kB, int64_t n, const double *w, double *out, int64_t ldo,
+                        uint32_t flags) {
+    PMC_REQUIRE(ctx != nullptr, "ctx is NULL");
+    return pmc_gram_impl(ctx, A, csA, kA, B, csB, kB, n, w, out, ldo, flags, ctx->ws, ctx->ws_bytes, 0);
+}
