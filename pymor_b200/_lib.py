@@ -1,0 +1,180 @@
+"""ctypes binding of libpymor_b200.so (the C ABI declared in include/pymor_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no sm_100a device is present, creating
+a :class:`DeviceContext` raises.  All pointers cross the boundary as plain integers.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+from pathlib import Path
+
+import numpy as np
+import torch
+
+PMC_OK = 0
+PMC_ERR_WORKSPACE = -3
+PMC_SYNC = 1
+PMC_SYMMETRIC = 2
+PMC_FORCE_SIMPLE = 4
+
+LIB_PATH = Path(__file__).resolve().parent / 'lib' / 'libpymor_b200.so'
+
+_P, _I64, _I32, _U32 = c_void_p, c_int64, c_int32, c_uint32
+
+# name -> argtypes (after the leading pmc_ctx*); every symbol of include/pymor_b200.h is listed here
+_CTX_FUNCS = {
+    'pmc_gram': [_P, _I64, _I32, _P, _I64, _I32, _I64, _P, _P, _I64, _U32],
+    'pmc_lincomb': [_P, _I64, _I32, _I64, _P, _I64, _I32, _P, _I64, _U32],
+    'pmc_pairwise_inner': [_P, _I64, _P, _I64, _I32, _I64, _P, _P, _U32],
+    'pmc_norm2': [_P, _I64, _I32, _I64, _P, _P, _U32],
+    'pmc_axpy': [_P, _I64, _P, _I64, _I32, _I64, _P, _I32, _U32],
+    'pmc_scal': [_P, _I64, _I32, _I64, _P, _I32, _U32],
+    'pmc_copy': [_P, _I64, _P, _I64, _I32, _I64, _U32],
+    'pmc_gather_cols': [_P, _I64, _P, _I64, _P, _I32, _I64, _U32],
+    'pmc_dofs': [_P, _I64, _I32, _I64, _P, _I32, _P, _U32],
+    'pmc_amax': [_P, _I64, _I32, _I64, _P, _P, _U32],
+    'pmc_diag_apply': [_P, _P, _I64, _P, _I64, _I32, _I64, _U32],
+    'pmc_csr_apply': [_I64, _P, _P, _P, _P, _I64, _P, _I64, _I32, _U32],
+    'pmc_csr_gram': [_I64, _P, _P, _P, _P, _I64, _I32, _P, _I64, _I32, _P, _I64, _U32],
+    'pmc_measure_fp64_peak': [c_int, c_double, _P],
+}
+_OTHER_FUNCS = {
+    'pmc_version': ([], c_int),
+    'pmc_last_error': ([], ctypes.c_char_p),
+    'pmc_ctx_create': ([c_int, _P, ctypes.POINTER(_P)], c_int),
+    'pmc_ctx_destroy': ([_P], c_int),
+    'pmc_ctx_set_workspace': ([_P, _P, c_size_t], c_int),
+    'pmc_ctx_workspace_needed': ([_P], c_size_t),
+    'pmc_ctx_sync': ([_P], c_int),
+    'pmc_ctx_sm_count': ([_P], c_int),
+    'pmc_ctx_launch_count': ([_P], c_int64),
+}
+EXPORTED_SYMBOLS = sorted(list(_CTX_FUNCS) + list(_OTHER_FUNCS))
+
+
+class PmcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree shared library and declare the prototypes.  Raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise PmcError(f'{LIB_PATH} not found: build it with `python -m pymor_b200.build` '
+                       '(nvcc, sm_100a).  There is no CPU fallback.')
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, args in _CTX_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_P] + args
+        fn.restype = c_int
+    for name, (args, res) in _OTHER_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def set_library_for_testing(lib):
+    """Inject an object exposing the same entry points (tests/emulated_lib.py) -- test use only."""
+    global _lib
+    _lib = lib
+    _contexts.clear()
+
+
+class DeviceContext:
+    """One ``pmc_ctx`` per device: stream, workspace and pinned result buffers.
+
+    Device memory (workspace included) is allocated through torch and lent to the library."""
+
+    def __init__(self, device):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        on_cuda = self.device.type == 'cuda'
+        if on_cuda:
+            index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self.device = torch.device('cuda', index)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        else:
+            index, stream = 0, 0      # only reachable with an injected test library
+        handle = _P()
+        rc = self.lib.pmc_ctx_create(index, stream, ctypes.byref(handle))
+        if rc != PMC_OK:
+            raise PmcError(f'pmc_ctx_create failed: {self._err()}')
+        self.handle = handle.value if isinstance(handle.value, int) else handle
+        self._pin = on_cuda
+        self._ws = None
+        self.ensure_workspace(64 << 20)
+        self._host_f64 = torch.empty(1 << 16, dtype=torch.float64, pin_memory=self._pin)
+        self._host_i64 = torch.empty(1 << 12, dtype=torch.int64, pin_memory=self._pin)
+
+    def _err(self):
+        msg = self.lib.pmc_last_error()
+        return msg.decode() if isinstance(msg, bytes) else str(msg)
+
+    def ensure_workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            rc = self.lib.pmc_ctx_set_workspace(self.handle, self._ws.data_ptr(), self._ws.numel())
+            if rc != PMC_OK:
+                raise PmcError(self._err())
+
+    def call(self, name, *args):
+        """Invoke ``name(ctx, *args)``; grows the workspace and retries on PMC_ERR_WORKSPACE."""
+        fn = getattr(self.lib, name)
+        rc = fn(self.handle, *args)
+        if rc == PMC_ERR_WORKSPACE:
+            need = int(self.lib.pmc_ctx_workspace_needed(self.handle))
+            self.ensure_workspace(need + (need >> 2))
+            rc = fn(self.handle, *args)
+        if rc != PMC_OK:
+            raise PmcError(f'{name} failed ({rc}): {self._err()}')
+
+    def host_f64(self, count):
+        """Pinned (device-writable) host buffer of at least ``count`` doubles."""
+        if self._host_f64.numel() < count:
+            self._host_f64 = torch.empty(int(count), dtype=torch.float64, pin_memory=self._pin)
+        return self._host_f64
+
+    def host_i64(self, count):
+        if self._host_i64.numel() < count:
+            self._host_i64 = torch.empty(int(count), dtype=torch.int64, pin_memory=self._pin)
+        return self._host_i64
+
+    def sync(self):
+        rc = self.lib.pmc_ctx_sync(self.handle)
+        if rc != PMC_OK:
+            raise PmcError(self._err())
+
+    @property
+    def sm_count(self):
+        return int(self.lib.pmc_ctx_sm_count(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pmc_ctx_launch_count(self.handle))
+
+    def measure_fp64_peak(self, use_dmma=True, ms=200.0):
+        out = np.zeros(1)
+        self.call('pmc_measure_fp64_peak', int(bool(use_dmma)), float(ms), out.ctypes.data)
+        return float(out[0])
+
+
+_contexts = {}
+
+
+def get_context(device) -> DeviceContext:
+    device = torch.device(device)
+    if device.type == 'cuda' and device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = DeviceContext(device)
+    return ctx

@@ -1,0 +1,159 @@
+"""Stand-alone drivers of the hot-path algorithms.
+
+These are the CALLERS of the backend.  With pyMOR installed use pyMOR's own functions -- they run
+unchanged on :class:`~pymor_b200.vectorarray.CudaVectorArray`.  On a box without pyMOR (the GPU box of
+this project) the functions below provide the same algorithms with the same names, arguments,
+defaults and error behaviour, written against the VectorArray/Operator interface only (they never
+touch raw data, like their reference counterparts):
+
+* :func:`gram_schmidt`          -- src/pymor/algorithms/gram_schmidt.py:13-122
+* :func:`method_of_snapshots`   -- src/pymor/algorithms/svd_va.py:20-99
+* :func:`qr_svd`                -- src/pymor/algorithms/svd_va.py:103-168
+* :func:`pod`                   -- src/pymor/algorithms/pod.py:16-90
+* :func:`project`               -- src/pymor/algorithms/projection.py:28-85 (rule ``action_apply_basis``)
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import scipy.linalg as spla
+
+logger = logging.getLogger('pymor_b200.algorithms')
+
+
+class AccuracyError(Exception):
+    """Raised when the result of :func:`gram_schmidt` fails the orthonormality check."""
+
+
+def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset=0,
+                 reiterate=True, reiteration_threshold=9e-1, check=True, check_tol=1e-3, copy=True):
+    """Modified Gram-Schmidt with re-iteration; vectors that are (numerically) zero or linearly
+    dependent are removed.  Returns ``Q`` or ``(Q, R)``."""
+    if copy:
+        A = A.copy()
+    k = len(A)
+    R = np.eye(k)
+    dropped = []
+    for i in range(offset, k):
+        v = A[i]
+        norm0 = v.norm(product)[0]
+        if norm0 <= atol:
+            logger.info('Removing vector %d of norm %g', i, norm0)
+            dropped.append(i)
+            continue
+        if i == 0:
+            v.scal(1 / norm0)
+            R[0, 0] = norm0
+            continue
+        cur = norm0
+        while True:
+            for j in range(i):
+                if j in dropped:
+                    continue
+                q = A[j]
+                p = q.pairwise_inner(v, product)[0]
+                v.axpy(-p, q)
+                R[j, i] += p
+            prev, cur = cur, v.norm(product)[0]
+            if cur <= rtol * norm0:
+                logger.info('Removing linearly dependent vector %d', i)
+                dropped.append(i)
+                break
+            if reiterate and cur < reiteration_threshold * prev:
+                logger.info('Orthonormalizing vector %d again', i)
+                continue
+            v.scal(1 / cur)
+            R[i, i] = cur
+            break
+    if dropped:
+        del A[dropped]
+        R = np.delete(R, dropped, axis=0)
+    if check:
+        m = len(A) - offset
+        err = A[offset:len(A)].inner(A, product)
+        err[:m, offset:len(A)] -= np.eye(m)
+        if err.size > 0:
+            worst = np.max(np.abs(err))
+            if worst >= check_tol:
+                raise AccuracyError(f'result not orthogonal (max err={worst})')
+    return (A, R) if return_R else A
+
+
+def _select_modes(s, modes, rtol, atol, l2_err):
+    above = np.nonzero(s >= max(rtol * s[0], atol))[0]
+    if above.size == 0:
+        return 0
+    tail_energy = np.concatenate((np.cumsum(s[::-1] ** 2)[::-1], [0.]))
+    n_err = int(np.nonzero(tail_energy <= l2_err ** 2)[0][0])
+    count = min(n_err, int(above[-1]) + 1)
+    return count if modes is None else min(count, modes)
+
+
+def method_of_snapshots(A, product=None, modes=None, rtol=1e-7, atol=0., l2_err=0.):
+    """SVD of ``A`` through the eigendecomposition of its (weighted) Gramian.  Returns
+    ``U`` (VectorArray of left singular vectors), ``s``, ``Vh``.  The small eigenproblem stays on
+    the host (LAPACK ``dsyevr`` via SciPy)."""
+    if A.dim == 0 or len(A) == 0:
+        return A.space.empty(), np.array([]), np.zeros((0, len(A)))
+    k = len(A)
+    G = A.gramian(product)
+    window = None if (modes is None or l2_err > 0.) else (max(k - modes, 0), k - 1)
+    evals, V = spla.eigh(G, overwrite_a=True, subset_by_index=window)
+    evals, V = evals[::-1], V[:, ::-1]
+    s = np.sqrt(np.clip(evals, a_min=0., a_max=None))
+    m = _select_modes(s, modes, rtol, atol, l2_err)
+    if m > A.dim:
+        logger.warning('Number of computed singular vectors larger than array dimension! Truncating ...')
+        m = A.dim
+    s, V = s[:m], V[:, :m]
+    return A.lincomb(V / s), s, V.conj().T
+
+
+def qr_svd(A, product=None, modes=None, rtol=4e-8, atol=0., l2_err=0.):
+    """SVD of ``A`` through Gram-Schmidt QR and the SVD of the small ``R`` factor."""
+    if A.dim == 0 or len(A) == 0:
+        return A.space.empty(), np.array([]), np.zeros((0, len(A)))
+    Q, R = gram_schmidt(A, product=product, return_R=True, check=False)
+    U2, s, Vh = spla.svd(R, lapack_driver='gesvd')
+    m = _select_modes(s, modes, rtol, atol, l2_err)
+    return Q.lincomb(U2[:, :m]), s[:m], Vh[:m]
+
+
+SVD_VA_METHODS = {'method_of_snapshots': method_of_snapshots, 'qr_svd': qr_svd}
+
+
+def pod(A, product=None, modes=None, rtol=1e-7, atol=0., l2_err=0., method='qr_svd', orth_tol=1e-10,
+        return_reduced_coefficients=False):
+    """Proper orthogonal decomposition of ``A``; re-orthonormalises the modes with
+    :func:`gram_schmidt` when their orthogonality error is not below ``orth_tol``."""
+    assert method in SVD_VA_METHODS
+    modes_va, svals, coeffs = SVD_VA_METHODS[method](A, product=product, modes=modes, rtol=rtol, atol=atol,
+                                                     l2_err=l2_err)
+    if modes_va.dim > 0 and len(modes_va) > 0 and np.isfinite(orth_tol):
+        err = np.max(np.abs(modes_va.inner(modes_va, product) - np.eye(len(modes_va))))
+        if err >= orth_tol:
+            logger.info('Reorthogonalizing POD modes ...')
+            gram_schmidt(modes_va, product=product, atol=0., rtol=0., copy=False)
+    if return_reduced_coefficients:
+        return modes_va, svals, coeffs
+    return modes_va, svals
+
+
+def project(op, range_basis, source_basis, product=None):
+    """Petrov-Galerkin projection of a linear, non-parametric operator.
+
+    Returns the projected matrix ``(len(range_basis), len(source_basis))`` as a NumPy array when both
+    bases are given (pyMOR wraps the same array in a ``NumpyMatrixOperator``); with only one basis the
+    VectorArray ``op.apply_adjoint(range_basis)`` resp. ``op.apply(source_basis)`` is returned."""
+    assert source_basis is None or source_basis in op.source
+    assert range_basis is None or range_basis in op.range
+    assert product is None or product.source == product.range == op.range
+    if range_basis is None and source_basis is None:
+        return op
+    rb = product.apply(range_basis) if (product is not None and range_basis is not None) else range_basis
+    if source_basis is None:
+        return op.apply_adjoint(rb)
+    if rb is None:
+        return op.apply(source_basis)
+    return op.apply2(rb, source_basis)

@@ -1,0 +1,586 @@
+"""CudaVectorSpace / CudaVectorArray: device-resident fp64 snapshot arrays behind pyMOR's
+VectorArray interface.
+
+Storage (mirrors ``NumpyVectorArrayImpl``'s Fortran-ordered ``(dim, len)`` ndarray, reference:
+src/pymor/vectorarrays/numpy.py:16-18, :264): one torch CUDA tensor of shape ``(capacity, ld)``,
+row ``i`` = vector ``i``, the ``dim`` DOFs of a vector contiguous, ``ld`` = ``dim`` rounded up to 16
+doubles (128 B) so that every vector is TMA- and 128-bit-load aligned.  torch is used for allocation,
+stream and DLPack interop only; all arithmetic runs in libpymor_b200.so (hand-written sm_100a
+kernels) through the C ABI of include/pymor_b200.h.  There is no CPU fallback.
+
+With a communicator the rows are sharded over ranks (one process per GPU) exactly like
+``MPIVectorArrayAutoComm`` (src/pymor/vectorarrays/mpi.py:316-445).
+
+Complex numbers: the north star is fp64; complex input raises ``NotImplementedError`` (pyMOR's own
+contract tests tolerate this for backends, src/pymortests/vectorarray.py:66-69).
+"""
+from __future__ import annotations
+
+from numbers import Number
+
+import numpy as np
+import torch
+
+from pymor_b200 import _lib
+from pymor_b200._lib import PMC_FORCE_SIMPLE, PMC_SYMMETRIC, PMC_SYNC
+from pymor_b200.dist import SingleRank, merge_amax, partition
+from pymor_b200.interface import HAVE_PYMOR, VectorArray, VectorArrayImpl, VectorSpace, create_random_values
+
+_ALIGN = 16  # doubles
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def _progression(ind, length):
+    """(start, step, count) if ``ind`` addresses an arithmetic progression of columns, else None."""
+    if ind is None:
+        return 0, 1, length
+    if type(ind) is slice:
+        r = range(*ind.indices(length))
+        return r.start, r.step, len(r)
+    count = len(ind)
+    if count == 0:
+        return 0, 1, 0
+    first = int(ind[0])
+    if count == 1:
+        return first, 1, 1
+    step = int(ind[1]) - first
+    prev = int(ind[1])
+    for v in ind[2:]:
+        if int(v) - prev != step:
+            return None
+        prev = int(v)
+    return first, step, count
+
+
+def _columns(ind, length):
+    """The addressed columns as a ``range`` or list."""
+    if ind is None:
+        return range(length)
+    if type(ind) is slice:
+        return range(*ind.indices(length))
+    return [int(i) for i in ind]
+
+
+def _overlap(a, b):
+    if len(a) == 0 or len(b) == 0:
+        return False
+    if len(a) == 1 and len(b) == 1:
+        return a[0] == b[0]
+    return not set(a).isdisjoint(b)
+
+
+def _runs(cols):
+    """Split a column list into maximal arithmetic progressions: (offset, start, step, count)."""
+    out, i, n = [], 0, len(cols)
+    while i < n:
+        if i + 1 == n:
+            out.append((i, cols[i], 1, 1))
+            break
+        step = cols[i + 1] - cols[i]
+        j = i + 1
+        while j + 1 < n and cols[j + 1] - cols[j] == step:
+            j += 1
+        if step == 0:           # never merge repeated columns into one writable run
+            out.append((i, cols[i], 1, 1))
+            i += 1
+            continue
+        out.append((i, cols[i], step, j - i + 1))
+        i = j + 1
+    return out
+
+
+def _consecutive_runs(cols):
+    """Maximal runs of consecutive integers in the sorted list ``cols``: (start, count)."""
+    out = []
+    for c in cols:
+        if out and out[-1][0] + out[-1][1] == c:
+            out[-1][1] += 1
+        else:
+            out.append([c, 1])
+    return out
+
+
+def _real_scalars(alpha, count):
+    """alpha (Number | ndarray (count,)) -> contiguous float64 host array of 1 or ``count`` values."""
+    a = np.asarray(alpha)
+    if np.iscomplexobj(a):
+        if np.any(a.imag != 0):
+            raise NotImplementedError('CudaVectorArray is real fp64; complex coefficients are not supported')
+        a = a.real
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    assert a.size in (1, count)
+    return a
+
+
+class CudaVectorArrayImpl(VectorArrayImpl):
+    """Backend object owning one device buffer (reference counterpart: numpy.py:14-211)."""
+
+    def __init__(self, space, buf, length):
+        self.space = space
+        self._buf = buf
+        self._len = int(length)
+
+    # -- storage helpers -------------------------------------------------------------------
+    @classmethod
+    def allocate(cls, space, count, reserve=0, zero=False):
+        cap = max(int(count), int(reserve), 1)
+        alloc = torch.zeros if zero else torch.empty
+        buf = alloc((cap, space.ld), dtype=torch.float64, device=space.device)
+        return cls(space, buf, count)
+
+    @property
+    def ld(self):
+        return self._buf.stride(0)
+
+    @property
+    def n(self):
+        return self.space.local_dim
+
+    def __len__(self):
+        return self._len
+
+    def _ptr(self, col=0):
+        return self._buf.data_ptr() + col * self._buf.stride(0) * 8
+
+    def _panel(self, ind):
+        """(ptr, column stride, count, keepalive) of a READ-ONLY panel; arbitrary index lists are
+        gathered into a temporary (numpy.py:21 fancy indexing does the same)."""
+        prog = _progression(ind, self._len)
+        if prog is not None:
+            start, step, count = prog
+            return self._ptr(start) if count else self._ptr(0), step * self.ld, count, self
+        tmp = self._gathered(_columns(ind, self._len))
+        return tmp._ptr(0), tmp.ld, tmp._len, tmp
+
+    def _gathered(self, cols, reserve=0):
+        new = CudaVectorArrayImpl.allocate(self.space, len(cols), reserve)
+        if len(cols) and self.n:
+            idx = np.ascontiguousarray(cols, dtype=np.int64)
+            self.space.ctx.call('pmc_gather_cols', new._ptr(0), new.ld, self._ptr(0), self.ld,
+                                idx.ctypes.data, len(cols), self.n, 0)
+        return new
+
+    def _copied(self, ind, reserve=0):
+        prog = _progression(ind, self._len)
+        if prog is None:
+            return self._gathered(_columns(ind, self._len), reserve)
+        start, step, count = prog
+        new = CudaVectorArrayImpl.allocate(self.space, count, reserve)
+        if count and self.n:
+            self.space.ctx.call('pmc_copy', new._ptr(0), new.ld, self._ptr(start), step * self.ld,
+                                count, self.n, 0)
+        return new
+
+    # -- VectorArrayImpl interface ------------------------------------------------------------
+    def copy(self, deep, ind):
+        return self._copied(ind)
+
+    def real(self, ind):
+        return self._copied(ind)
+
+    def conj(self, ind):
+        return self._copied(ind)
+
+    def imag(self, ind):
+        return CudaVectorArrayImpl.allocate(self.space, self.len_ind(ind), zero=True)
+
+    def to_numpy(self, ensure_copy, ind):
+        prog = _progression(ind, self._len)
+        if prog is not None and prog[1] == 1:
+            block = self._buf[prog[0]:prog[0] + prog[2], :self.n]
+        else:
+            tmp = self._copied(ind)
+            block = tmp._buf[:tmp._len, :self.n]
+        comm = self.space.comm
+        if comm.size > 1:
+            nmax = int(self.space.local_dims.max())
+            padded = torch.zeros((block.shape[0], nmax), dtype=torch.float64, device=self.space.device)
+            padded[:, :self.n] = block
+            parts = comm.allgather(padded)
+            block = torch.cat([p[:, :int(d)] for p, d in zip(parts, self.space.local_dims)], dim=1)
+        host = block.to('cpu').contiguous().numpy()      # (k, dim) C-order == (dim, k) F-order
+        return host.T
+
+    def delete(self, ind):
+        if ind is None:
+            self._len = 0
+            return
+        # `ind` arrives un-normalised here (interface.py:252-259): int, slice or list, negatives allowed
+        if isinstance(ind, Number):
+            ind = [int(ind)]
+        drop = {i % self._len for i in _columns(ind, self._len)} if self._len else set()
+        keep = [c for c in range(self._len) if c not in drop]
+        ctx, pos = self.space.ctx, 0
+        # in-place compaction; a run is moved in chunks no longer than its shift so that source and
+        # destination columns of one launch never overlap
+        for start, count in _consecutive_runs(keep):
+            shift = start - pos
+            if shift and self.n:
+                for off in range(0, count, shift):
+                    c = min(shift, count - off)
+                    ctx.call('pmc_copy', self._ptr(pos + off), self.ld, self._ptr(start + off), self.ld,
+                             c, self.n, 0)
+            pos += count
+        self._len = len(keep)
+
+    def append(self, other, remove_from_other, oind):
+        k_other = other.len_ind(oind)
+        if k_other == 0:
+            return
+        if other is self:
+            src = self._copied(oind)
+            ptr, cs, keep = src._ptr(0), src.ld, src
+        else:
+            ptr, cs, _, keep = other._panel(oind)
+        need = self._len + k_other
+        if need > self._buf.shape[0]:
+            cap = max(need, int(self._buf.shape[0] * 1.5) + 1)
+            grown = torch.empty((cap, self.ld), dtype=torch.float64, device=self.space.device)
+            if self._len and self.n:
+                self.space.ctx.call('pmc_copy', grown.data_ptr(), self.ld, self._ptr(0), self.ld,
+                                    self._len, self.n, 0)
+            self._buf = grown
+        if self.n:
+            self.space.ctx.call('pmc_copy', self._ptr(self._len), self.ld, ptr, cs, k_other, self.n, 0)
+        del keep
+        self._len = need
+        if remove_from_other:
+            other.delete(oind)
+
+    def scal(self, alpha, ind):
+        cols = _columns(ind, self._len)
+        if len(cols) == 0 or self.n == 0:
+            _real_scalars(alpha, len(cols))
+            return
+        a = _real_scalars(alpha, len(cols))
+        ctx = self.space.ctx
+        for off, start, step, count in self._write_runs(ind, cols):
+            if a.size == 1:
+                ctx.call('pmc_scal', self._ptr(start), step * self.ld, count, self.n, a.ctypes.data, 1, 0)
+            else:
+                ctx.call('pmc_scal', self._ptr(start), step * self.ld, count, self.n,
+                         a.ctypes.data + 8 * off, count, 0)
+
+    def _write_runs(self, ind, cols):
+        prog = _progression(ind, self._len)
+        if prog is not None and (prog[1] != 0 or prog[2] <= 1):
+            return [(0, prog[0], prog[1] if prog[2] > 1 else 1, prog[2])]
+        return _runs(list(cols))
+
+    def axpy(self, alpha, x, ind, xind):
+        cols = _columns(ind, self._len)
+        k = len(cols)
+        a = _real_scalars(alpha, k)
+        if k == 0 or self.n == 0:
+            return
+        xcols = _columns(xind, x._len)
+        if x._buf is self._buf and _overlap(cols, xcols):
+            # NumPy evaluates the right-hand side first (numpy.py:138): snapshot aliased operands
+            x = x._copied(xind)
+            xind = None
+        xptr, xcs, kx, keep = x._panel(xind)
+        if kx == 1 and k > 1:
+            xcs = 0
+        ctx = self.space.ctx
+        for off, start, step, count in self._write_runs(ind, cols):
+            xp = xptr + 8 * off * xcs
+            if a.size == 1:
+                ctx.call('pmc_axpy', self._ptr(start), step * self.ld, xp, xcs, count, self.n,
+                         a.ctypes.data, 1, 0)
+            else:
+                ctx.call('pmc_axpy', self._ptr(start), step * self.ld, xp, xcs, count, self.n,
+                         a.ctypes.data + 8 * off, count, 0)
+        del keep
+
+    def inner(self, other, ind, oind, weight_ptr=0):
+        pa, csa, ka, keep_a = self._panel(ind)
+        symmetric = other is self and _same_index(ind, oind)
+        if symmetric:
+            pb, csb, kb, keep_b = pa, csa, ka, keep_a
+        else:
+            pb, csb, kb, keep_b = other._panel(oind)
+        if ka == 0 or kb == 0:
+            return np.zeros((ka, kb), order='F')
+        sp = self.space
+        out, flags = sp.reduction_target(ka * kb)
+        if symmetric:
+            flags |= PMC_SYMMETRIC
+        sp.ctx.call('pmc_gram', pa, csa, ka, pb, csb, kb, self.n, weight_ptr, out.data_ptr(), ka,
+                    flags | sp.kernel_flags)
+        del keep_a, keep_b
+        return sp.reduction_result(out, ka * kb).reshape((ka, kb), order='F')
+
+    def gramian(self, ind):
+        return self.inner(self, ind, ind)
+
+    def pairwise_inner(self, other, ind, oind, weight_ptr=0):
+        pa, csa, ka, keep_a = self._panel(ind)
+        if ka == 0:
+            return np.zeros(0)
+        sp = self.space
+        out, flags = sp.reduction_target(ka)
+        if other is self and _same_index(ind, oind):
+            sp.ctx.call('pmc_norm2', pa, csa, ka, self.n, weight_ptr, out.data_ptr(), flags)
+        else:
+            pb, csb, kb, keep_b = other._panel(oind)
+            assert ka == kb
+            sp.ctx.call('pmc_pairwise_inner', pa, csa, pb, csb, ka, self.n, weight_ptr, out.data_ptr(), flags)
+            del keep_b
+        del keep_a
+        return sp.reduction_result(out, ka)
+
+    def norm2(self, ind, weight_ptr=0):
+        pa, csa, ka, keep_a = self._panel(ind)
+        if ka == 0:
+            return np.zeros(0)
+        sp = self.space
+        out, flags = sp.reduction_target(ka)
+        sp.ctx.call('pmc_norm2', pa, csa, ka, self.n, weight_ptr, out.data_ptr(), flags)
+        del keep_a
+        return sp.reduction_result(out, ka)
+
+    def norm(self, ind):
+        return np.sqrt(self.norm2(ind))
+
+    def lincomb(self, coefficients, ind):
+        pa, csa, k, keep = self._panel(ind)
+        coefficients = np.asarray(coefficients)
+        if np.iscomplexobj(coefficients):
+            if np.any(coefficients.imag != 0):
+                raise NotImplementedError('complex lincomb coefficients are not supported')
+            coefficients = coefficients.real
+        assert coefficients.ndim == 2 and coefficients.shape[0] == k
+        m = coefficients.shape[1]
+        new = CudaVectorArrayImpl.allocate(self.space, m)
+        if m == 0 or self.n == 0:
+            return new
+        ldc = max(_round_up(k, 2), 2)
+        host = np.zeros((ldc, m), dtype=np.float64, order='F')
+        host[:k] = coefficients
+        ct = torch.from_numpy(host.T).to(self.space.device)      # (m, ldc) C-order = F-ordered (ldc, m)
+        self.space.ctx.call('pmc_lincomb', pa, csa, k, self.n, ct.data_ptr(), ldc, m, new._ptr(0), new.ld,
+                            self.space.kernel_flags)
+        # `ct` is released in stream order by torch's caching allocator (same stream as the kernel)
+        del keep
+        return new
+
+    def dofs(self, dof_indices, ind):
+        pa, csa, k, keep = self._panel(ind)
+        sp = self.space
+        idx = np.ascontiguousarray(dof_indices, dtype=np.int64)
+        nd = idx.size
+        if nd == 0 or k == 0:
+            return np.zeros((nd, k), order='F')
+        if sp.comm.size == 1:
+            out = sp.ctx.host_f64(nd * k)
+            sp.ctx.call('pmc_dofs', pa, csa, k, self.n, idx.ctypes.data, nd, out.data_ptr(), PMC_SYNC)
+            return np.array(out[:nd * k].numpy()).reshape((nd, k), order='F')
+        # sharded: the owner contributes the value, everybody else zero, then sum (mpi.py:421-432)
+        mine = np.nonzero((idx >= sp.offset) & (idx < sp.offset + self.n))[0]
+        local = torch.zeros((k, nd), dtype=torch.float64, device=sp.device)
+        if mine.size:
+            loc_idx = np.ascontiguousarray(idx[mine] - sp.offset)
+            tmp = torch.empty((k, mine.size), dtype=torch.float64, device=sp.device)
+            sp.ctx.call('pmc_dofs', pa, csa, k, self.n, loc_idx.ctypes.data, mine.size, tmp.data_ptr(), 0)
+            local[:, torch.from_numpy(mine).to(sp.device)] = tmp
+        sp.comm.allreduce_sum_(local)
+        del keep
+        return np.asfortranarray(local.to('cpu').numpy().T)
+
+    def amax(self, ind):
+        pa, csa, k, keep = self._panel(ind)
+        sp = self.space
+        if k == 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0)
+        if sp.comm.size == 1:
+            oi, ov = sp.ctx.host_i64(k), sp.ctx.host_f64(k)
+            sp.ctx.call('pmc_amax', pa, csa, k, self.n, oi.data_ptr(), ov.data_ptr(), PMC_SYNC)
+            return np.array(oi[:k].numpy()), np.array(ov[:k].numpy())
+        oi = torch.zeros(k, dtype=torch.int64, device=sp.device)
+        ov = torch.full((k,), -1.0, dtype=torch.float64, device=sp.device)
+        if self.n:
+            sp.ctx.call('pmc_amax', pa, csa, k, self.n, oi.data_ptr(), ov.data_ptr(), 0)
+            oi += sp.offset
+        inds = torch.stack(sp.comm.allgather(oi)).to('cpu').numpy()
+        vals = torch.stack(sp.comm.allgather(ov)).to('cpu').numpy()
+        del keep
+        return merge_amax(inds, vals)
+
+
+def _same_index(a, b):
+    if a is b:
+        return True
+    if type(a) is not type(b):
+        return False
+    return a == b
+
+
+class CudaVectorArray(VectorArray):
+    """|VectorArray| whose vectors live in B200 HBM."""
+
+    impl_type = CudaVectorArrayImpl
+
+    def to_torch(self):
+        """Zero-copy ``(len, local_dim)`` torch view of the (non-view) array's shard."""
+        impl = self.impl
+        prog = _progression(self.ind, impl._len)
+        if prog is None or prog[1] < 1:
+            impl, prog = impl._copied(self.ind), (0, 1, self._len)
+        start, step, count = prog
+        return impl._buf[start:start + step * count:step, :impl.n]
+
+    def __dlpack__(self, *args, **kwargs):
+        return self.to_torch().__dlpack__(*args, **kwargs)
+
+    def __dlpack_device__(self):
+        return self.to_torch().__dlpack_device__()
+
+    def __str__(self):
+        return f'CudaVectorArray(len={len(self)}, dim={self.dim}, device={self.space.device})'
+
+
+class CudaVectorSpace(VectorSpace):
+    """|VectorSpace| of :class:`CudaVectorArray` (reference counterpart: numpy.py:242-337).
+
+    Parameters
+    ----------
+    dim
+        GLOBAL number of DOFs.
+    device
+        torch device of this rank (default: current CUDA device).
+    comm
+        ``None`` (single GPU) or a :class:`pymor_b200.dist.ProcessGroupComm`: rows are split evenly
+        over the ranks.
+    id
+        See pyMOR's ``VectorSpace.id``.
+    """
+
+    def __init__(self, dim, device=None, comm=None, id=None):
+        self.dim = int(dim)
+        self.id = id
+        self._comm = comm if comm is not None else SingleRank()
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else 'cuda'
+        self._ctx = _lib.get_context(device)           # raises without library / device
+        self.device = self._ctx.device
+        dims, offsets = partition(self.dim, self._comm.size)
+        self._local_dims = dims
+        self._local_dim = int(dims[self._comm.rank])
+        self._offset = int(offsets[self._comm.rank])
+        self._ld = max(_round_up(self._local_dim, _ALIGN), _ALIGN)
+        self._red_dev = None
+        self._kernel_flags = 0
+        self._host_np = None
+
+    # read-only views of the private state (the pyMOR base class freezes public attributes)
+    ctx = property(lambda self: self._ctx)
+    local_dim = property(lambda self: self._local_dim)
+    local_dims = property(lambda self: self._local_dims)
+    offset = property(lambda self: self._offset)
+    ld = property(lambda self: self._ld)
+    kernel_flags = property(lambda self: self._kernel_flags)
+
+    comm = property(lambda self: self._comm)
+
+    def force_generic_kernels(self, enable=True):
+        """Route gramian/lincomb through the generic kernels (test hook for kernel cross-checks)."""
+        self._kernel_flags = PMC_FORCE_SIMPLE if enable else 0
+
+    # -- reductions: single GPU -> kernel writes pinned host memory; sharded -> device + all-reduce
+    def reduction_target(self, count):
+        if self._comm.size == 1:
+            return self._ctx.host_f64(count), PMC_SYNC
+        if self._red_dev is None or self._red_dev.numel() < count:
+            self._red_dev = torch.empty(max(int(count), 4096), dtype=torch.float64, device=self.device)
+        return self._red_dev, 0
+
+    def reduction_result(self, buf, count):
+        if self._comm.size == 1:
+            host = self._host_np
+            if host is None or host[0] is not buf:
+                host = self._host_np = (buf, buf.numpy())
+            return host[1][:count].copy()
+        part = buf[:count]
+        self._comm.allreduce_sum_(part)
+        return part.to('cpu').numpy().copy()
+
+    # -- factory ------------------------------------------------------------------------------
+    def __eq__(self, other):
+        return (type(other) is type(self) and self.dim == other.dim and self.id == other.id
+                and self.device == other.device and self._comm == other._comm)
+
+    def __hash__(self):
+        return hash((self.dim, self.id, str(self.device)))
+
+    def zeros(self, count=1, reserve=0):
+        assert count >= 0 and reserve >= 0
+        return CudaVectorArray(self, CudaVectorArrayImpl.allocate(self, count, reserve, zero=True))
+
+    def full(self, value, count=1, reserve=0):
+        assert count >= 0 and reserve >= 0
+        if isinstance(value, complex) or np.iscomplexobj(value):
+            raise NotImplementedError('complex values are not supported')
+        impl = CudaVectorArrayImpl.allocate(self, count, reserve)
+        impl._buf[:count].fill_(float(value))
+        return CudaVectorArray(self, impl)
+
+    def random(self, count=1, distribution='uniform', reserve=0, **kwargs):
+        """Host-generated through pyMOR's global RNG, so that inputs are bit-identical with
+        ``NumpyVectorSpace.random`` (interface.py:986-1007, numpy.py:272-277)."""
+        assert count >= 0 and reserve >= 0
+        values = create_random_values((self.dim, count), distribution, **kwargs)
+        return self._upload(values, reserve)
+
+    def random_device(self, count=1, seed=0, distribution='normal', scale=1.0, reserve=0):
+        """Device-side generation (torch Philox) for full-size benchmark inputs; per-rank seed."""
+        impl = CudaVectorArrayImpl.allocate(self, count, reserve)
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(int(seed) * 1000003 + self._comm.rank)
+        view = impl._buf[:count, :self._local_dim]
+        if distribution == 'normal':
+            view.normal_(0.0, scale, generator=gen)
+        else:
+            view.uniform_(0.0, scale, generator=gen)
+        return CudaVectorArray(self, impl)
+
+    def _upload(self, data, reserve=0):
+        data = np.asarray(data)
+        if np.iscomplexobj(data):
+            raise NotImplementedError('CudaVectorArray is real fp64; complex data is not supported')
+        if data.ndim == 1:
+            data = data.reshape((-1, 1))
+        assert data.ndim == 2 and data.shape[0] == self.dim
+        count = data.shape[1]
+        impl = CudaVectorArrayImpl.allocate(self, count, reserve)
+        if count and self._local_dim:
+            rows = np.ascontiguousarray(data[self._offset:self._offset + self._local_dim].T, dtype=np.float64)
+            impl._buf[:count, :self._local_dim].copy_(torch.from_numpy(rows))
+        return CudaVectorArray(self, impl)
+
+    def from_numpy(self, data, ensure_copy=False):
+        """``data`` is the GLOBAL ``(dim, len)`` array; always copies (host -> device)."""
+        return self._upload(data)
+
+    def make_array(self, obj):
+        """Adopt raw backend data: a ``(len, local_dim)`` fp64 CUDA tensor or any ``__dlpack__``
+        producer of one (zero-copy when 16-byte aligned with an even row stride), or a NumPy array
+        of shape ``(dim, len)``."""
+        if isinstance(obj, np.ndarray):
+            return self._upload(obj)
+        t = obj if isinstance(obj, torch.Tensor) else torch.from_dlpack(obj)
+        assert t.dtype == torch.float64 and t.dim() == 2 and t.shape[1] == self._local_dim
+        assert t.device == self.device
+        ok = (t.shape[0] > 0 and t.shape[1] > 0 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]
+              and t.stride(0) % 2 == 0 and t.data_ptr() % 16 == 0)
+        if ok:
+            return CudaVectorArray(self, CudaVectorArrayImpl(self, t, t.shape[0]))
+        impl = CudaVectorArrayImpl.allocate(self, t.shape[0])
+        if t.shape[0]:
+            impl._buf[:t.shape[0], :self._local_dim].copy_(t)
+        return CudaVectorArray(self, impl)
+
+    def __repr__(self):
+        return f'CudaVectorSpace(dim={self.dim}, device={self.device!s}, ranks={self._comm.size})'

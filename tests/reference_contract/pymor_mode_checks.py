@@ -1,0 +1,107 @@
+"""pyMOR's OWN algorithms on CudaVectorArray (collected only through run_contract.py, which puts the
+reference on sys.path first so that the CUDA classes subclass pyMOR's real base classes).
+
+Each check runs the unmodified reference function twice -- on NumpyVectorArray/NumpyMatrixOperator
+and on CudaVectorArray/Cuda*Operator built from the same bits -- and compares.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+from pymor.algorithms.chol_qr import shifted_chol_qr
+from pymor.algorithms.gram_schmidt import gram_schmidt
+from pymor.algorithms.pod import pod
+from pymor.algorithms.projection import project
+from pymor.algorithms.svd_va import method_of_snapshots, qr_svd
+from pymor.core.logger import set_log_levels
+from pymor.operators.constructions import LincombOperator, VectorOperator
+from pymor.operators.interface import Operator
+from pymor.operators.numpy import NumpyMatrixOperator
+from pymor.vectorarrays.interface import VectorArray, VectorSpace
+from pymor.vectorarrays.numpy import NumpyVectorSpace
+
+from pymor_b200.interface import HAVE_PYMOR
+from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+from pymor_b200.vectorarray import CudaVectorArray, CudaVectorSpace
+
+set_log_levels({'pymor': 'ERROR'})
+DEVICE = 'cuda' if __import__('torch').cuda.is_available() else 'cpu'
+
+
+def mass(n):
+    h = 1.0 / (n + 1)
+    return sps.diags([np.full(n - 1, h / 6), np.full(n, 4 * h / 6), np.full(n - 1, h / 6)], [-1, 0, 1]).tocsr()
+
+
+def make(dim, k, seed, kind):
+    rng = np.random.default_rng(seed)
+    A = np.asfortranarray(rng.standard_normal((dim, k)) + 2 * rng.standard_normal((dim, 1)))
+    nsp, csp = NumpyVectorSpace(dim), CudaVectorSpace(dim, device=DEVICE)
+    if kind == 'euclid':
+        return A, nsp, csp, None, None
+    if kind == 'diag':
+        w = rng.uniform(0.5, 1.5, dim)
+        return A, nsp, csp, NumpyMatrixOperator(sps.diags(w).tocsr()), CudaDiagonalOperator(w, csp)
+    M = mass(dim)
+    return A, nsp, csp, NumpyMatrixOperator(M), CudaCsrOperator(M, csp)
+
+
+def test_subclassing():
+    assert HAVE_PYMOR
+    assert issubclass(CudaVectorArray, VectorArray) and issubclass(CudaVectorSpace, VectorSpace)
+    assert issubclass(CudaCsrOperator, Operator) and issubclass(CudaDiagonalOperator, Operator)
+
+
+@pytest.mark.parametrize('kind', ['euclid', 'diag', 'csr'])
+def test_gram_schmidt(kind):
+    A, nsp, csp, nprod, cprod = make(157, 12, 1, kind)
+    Qn, Rn = gram_schmidt(nsp.from_numpy(A.copy()), product=nprod, return_R=True)
+    Qc, Rc = gram_schmidt(csp.from_numpy(A), product=cprod, return_R=True)
+    np.testing.assert_allclose(Qc.to_numpy(), Qn.to_numpy(), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(Rc, Rn, rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize('kind', ['euclid', 'diag', 'csr'])
+@pytest.mark.parametrize('method', ['method_of_snapshots', 'qr_svd'])
+def test_pod(kind, method):
+    A, nsp, csp, nprod, cprod = make(203, 9, 2, kind)
+    Un, sn = pod(nsp.from_numpy(A.copy()), product=nprod, method=method)
+    Uc, sc = pod(csp.from_numpy(A), product=cprod, method=method)
+    np.testing.assert_allclose(sc, sn, rtol=1e-10)
+    G = nsp.from_numpy(Uc.to_numpy()).inner(Un, nprod)
+    np.testing.assert_allclose(np.abs(G), np.eye(len(Un)), atol=1e-8)
+    svd = {'method_of_snapshots': method_of_snapshots, 'qr_svd': qr_svd}[method]
+    U, s, Vh = svd(csp.from_numpy(A), product=cprod)
+    np.testing.assert_allclose(U.lincomb(np.diag(s) @ Vh).to_numpy(), A, atol=1e-9)
+
+
+def test_project_and_lincomb_operator():
+    A, nsp, csp, nprod, cprod = make(120, 7, 3, 'csr')
+    rng = np.random.default_rng(5)
+    M1 = (sps.random(120, 120, density=0.05, random_state=1) + sps.eye(120)).tocsr()
+    M2 = mass(120)
+    V = np.asfortranarray(rng.standard_normal((120, 5)))
+    for ops_n, ops_c in [((NumpyMatrixOperator(M1),), (CudaCsrOperator(M1, csp),)),
+                         ((NumpyMatrixOperator(M1), NumpyMatrixOperator(M2)),
+                          (CudaCsrOperator(M1, csp), CudaCsrOperator(M2, csp)))]:
+        if len(ops_n) == 1:
+            on, oc = ops_n[0], ops_c[0]
+        else:
+            on, oc = LincombOperator(ops_n, [1.5, -0.5]), LincombOperator(ops_c, [1.5, -0.5])
+        pn = project(on, nsp.from_numpy(V.copy()), nsp.from_numpy(A.copy()), product=nprod)
+        pc = project(oc, csp.from_numpy(V), csp.from_numpy(A), product=cprod)
+        mn = pn.matrix if hasattr(pn, 'matrix') else pn.assemble().matrix
+        mc = pc.matrix if hasattr(pc, 'matrix') else pc.assemble().matrix
+        np.testing.assert_allclose(mc, mn, rtol=1e-11, atol=1e-12)
+    # right-hand side functional: project(VectorOperator(f), RB, None)
+    f = rng.standard_normal((120, 1))
+    pn = project(VectorOperator(nsp.from_numpy(f.copy())), nsp.from_numpy(A.copy()), None)
+    pc = project(VectorOperator(csp.from_numpy(f)), csp.from_numpy(A), None)
+    np.testing.assert_allclose(pc.matrix, pn.matrix, rtol=1e-11, atol=1e-12)
+
+
+def test_shifted_chol_qr_next_row_N1():
+    A, nsp, csp, nprod, cprod = make(300, 10, 4, 'diag')
+    Qn, Rn = shifted_chol_qr(nsp.from_numpy(A.copy()), product=nprod, return_R=True)
+    Qc, Rc = shifted_chol_qr(csp.from_numpy(A), product=cprod, return_R=True)
+    np.testing.assert_allclose(Rc, Rn, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(Qc.to_numpy(), Qn.to_numpy(), atol=1e-9)

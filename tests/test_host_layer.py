@@ -1,0 +1,314 @@
+"""Host-side logic of the CUDA backend on CPU (no GPU needed).
+
+The C ABI is served by tests/emulated_lib.py (NumPy) -- see that module's docstring.  What is under
+test here is everything ABOVE the boundary: index/view normalisation, copy-on-write, aliasing,
+capacity growth, in-place compaction on delete, operator fusion dispatch, the stand-alone algorithm
+drivers, and -- when /root/reference is present -- the reference's own contract suite and pyMOR's own
+algorithms running on CudaVectorArray.
+"""
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from conftest import HAVE_REFERENCE, ROOT, csr_from, load_golden
+from emulated_lib import EmulatedLib
+from oracle import numpy_path as O
+
+from pymor_b200 import _lib, algorithms as alg
+
+
+@pytest.fixture
+def emu():
+    lib = EmulatedLib()
+    _lib.set_library_for_testing(lib)
+    yield lib
+    _lib.set_library_for_testing(None)
+
+
+def space_of(dim):
+    from pymor_b200.vectorarray import CudaVectorSpace
+    return CudaVectorSpace(dim, device='cpu')
+
+
+def test_no_cpu_fallback_without_library_or_gpu():
+    """Without an injected test library the product must fail loudly on a box without a B200."""
+    _lib.set_library_for_testing(None)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from pymor_b200.vectorarray import CudaVectorSpace
+    with pytest.raises(Exception):
+        CudaVectorSpace(10)
+
+
+INDS = [None, slice(1, 6, 2), slice(5, 0, -2), [4, 0, 2], [3, 3, 1], [2], [], slice(0, 0)]
+
+
+def np_ind(A, ind):
+    return A if ind is None else A[:, ind]
+
+
+def va_ind(V, ind):
+    return V if ind is None else V[ind]
+
+
+@pytest.mark.parametrize('dim', [0, 1, 7, 37])
+def test_reductions_and_views(emu, rng, dim):
+    sp = space_of(dim)
+    A, B = rng.standard_normal((dim, 7)), rng.standard_normal((dim, 7))
+    VA, VB = sp.from_numpy(A), sp.from_numpy(B)
+    np.testing.assert_array_equal(VA.to_numpy(), A)
+    for i1 in INDS:
+        a, va = np_ind(A, i1), va_ind(VA, i1)
+        np.testing.assert_allclose(va.norm(), O.norm(a), atol=1e-14)
+        np.testing.assert_allclose(va.norm2(), O.norm2(a), atol=1e-14)
+        g = va.gramian()
+        np.testing.assert_allclose(g, O.gramian(a), atol=1e-13)
+        assert g.flags.f_contiguous or g.size <= 1
+        np.testing.assert_array_equal(g, g.T)
+        for i2 in INDS:
+            b, vb = np_ind(B, i2), va_ind(VB, i2)
+            np.testing.assert_allclose(va.inner(vb), O.inner(a, b), atol=1e-13)
+            np.testing.assert_allclose(va.inner(va_ind(VA, i2)), O.inner(a, np_ind(A, i2)), atol=1e-13)
+            if a.shape[1] == b.shape[1]:
+                np.testing.assert_allclose(va.pairwise_inner(vb), O.pairwise_inner(a, b), atol=1e-13)
+        if dim:
+            idx, val = va.amax()
+            oi, ov = O.amax(a)
+            np.testing.assert_array_equal(idx, oi)
+            np.testing.assert_array_equal(val, ov)
+            dofs = [0, dim - 1, dim // 2, 0]
+            np.testing.assert_array_equal(va.dofs(dofs), O.dofs(a, dofs))
+
+
+def test_lincomb_and_coefficient_layouts(emu, rng):
+    sp = space_of(23)
+    A = rng.standard_normal((23, 6))
+    VA = sp.from_numpy(A)
+    C = rng.standard_normal((6, 4))
+    for coeffs in (C, np.asfortranarray(C), C[:, ::-1], C.astype(np.float32).astype(np.float64), C[:, :0],
+                   np.arange(6)):
+        np.testing.assert_allclose(VA.lincomb(coeffs).to_numpy(), O.lincomb(A, coeffs), atol=1e-13)
+    np.testing.assert_allclose(VA[[5, 1, 1]].lincomb(C[:3]).to_numpy(), O.lincomb(A[:, [5, 1, 1]], C[:3]), atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        VA.lincomb(C * 1j)
+
+
+def test_axpy_scal_aliasing_and_index_forms(emu, rng):
+    sp = space_of(19)
+    A, B = rng.standard_normal((19, 7)), rng.standard_normal((19, 7))
+    al = rng.standard_normal(7)
+    VA, VB = sp.from_numpy(A), sp.from_numpy(B)
+    # scalar / per-column alpha, broadcast x
+    Y = VA.copy(); Y.axpy(0.5, VB); np.testing.assert_allclose(Y.to_numpy(), A + 0.5 * B, atol=1e-14)
+    Y = VA.copy(); Y.axpy(al, VB[2]); np.testing.assert_allclose(Y.to_numpy(), A + B[:, [2]] * al, atol=1e-14)
+    Y = VA.copy(); Y.axpy(np.arange(7), VB); np.testing.assert_allclose(Y.to_numpy(), A + B * np.arange(7), atol=1e-14)
+    # x is a permuted view of self: NumPy semantics = right-hand side evaluated first
+    Y = VA.copy(); Y.axpy(2.0, Y[::-1]); np.testing.assert_allclose(Y.to_numpy(), A + 2 * A[:, ::-1], atol=1e-14)
+    Y = VA.copy(); Y[[0, 3, 5]].axpy(al[:3], Y[[3, 5, 6]])
+    ref = A.copy(); ref[:, [0, 3, 5]] += A[:, [3, 5, 6]] * al[:3]
+    np.testing.assert_allclose(Y.to_numpy(), ref, atol=1e-14)
+    # disjoint views of the same array do not snapshot (the Gram-Schmidt inner step)
+    Y = VA.copy(); Y.scal(1.0)
+    before = emu.calls.count('pmc_copy')
+    Y[4].axpy(-0.3, Y[1])
+    assert emu.calls.count('pmc_copy') == before
+    ref = A.copy(); ref[:, 4] -= 0.3 * A[:, 1]
+    np.testing.assert_allclose(Y.to_numpy(), ref, atol=1e-14)
+    # scal: slices with negative step, irregular lists, int dtype
+    Y = VA.copy(); Y[5:0:-2].scal(np.array([2, 3, 4])); ref = A.copy(); ref[:, 5:0:-2] *= [2, 3, 4]
+    np.testing.assert_allclose(Y.to_numpy(), ref, atol=1e-14)
+    Y = VA.copy(); Y[[6, 0, 1, 4]].scal(al[:4]); ref = A.copy(); ref[:, [6, 0, 1, 4]] *= al[:4]
+    np.testing.assert_allclose(Y.to_numpy(), ref, atol=1e-14)
+    with pytest.raises(NotImplementedError):
+        VA.copy().scal(1j)
+    with pytest.raises(Exception):
+        VA[[1, 1]].scal(2.0)          # repeated indices are not writable
+
+
+def test_cow_append_delete_growth(emu, rng):
+    sp = space_of(11)
+    A, B = rng.standard_normal((11, 5)), rng.standard_normal((11, 4))
+    VA, VB = sp.from_numpy(A), sp.from_numpy(B)
+    C = VA.copy()
+    assert C.impl is VA.impl                       # lazy copy
+    C.scal(2.0)
+    assert C.impl is not VA.impl                   # copy on first write
+    np.testing.assert_array_equal(VA.to_numpy(), A)
+    np.testing.assert_allclose(C.to_numpy(), 2 * A)
+    V = sp.empty(reserve=2)
+    for _ in range(3):                             # growth beyond the reserve
+        V.append(VB)
+    V.append(V[[1, 0]])                            # append a view of itself
+    ref = np.hstack([B, B, B, B[:, [1, 0]]])
+    np.testing.assert_array_equal(V.to_numpy(), ref)
+    del V[[0, 2, 3, 9, -1]]
+    keep = [i for i in range(ref.shape[1]) if i not in (0, 2, 3, 9, ref.shape[1] - 1)]
+    np.testing.assert_array_equal(V.to_numpy(), ref[:, keep])
+    del V[1:4]
+    np.testing.assert_array_equal(V.to_numpy(), np.delete(ref[:, keep], slice(1, 4), axis=1))
+    W = sp.from_numpy(B)
+    X = sp.empty()
+    X.append(W[1:3], remove_from_other=True)
+    assert len(W) == 2 and len(X) == 2
+    np.testing.assert_array_equal(W.to_numpy(), B[:, [0, 3]])
+    np.testing.assert_array_equal(X.to_numpy(), B[:, 1:3])
+    with pytest.raises(NotImplementedError):
+        sp.from_numpy(A * (1 + 1j))
+
+
+@pytest.mark.parametrize('kind', ['diag', 'csr'])
+def test_product_operators_fused_paths(emu, rng, kind):
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    dim = 41
+    sp = space_of(dim)
+    A, B = rng.standard_normal((dim, 6)), rng.standard_normal((dim, 4))
+    VA, VB = sp.from_numpy(A), sp.from_numpy(B)
+    if kind == 'diag':
+        w = rng.uniform(0.5, 1.5, dim)
+        W, op = w, CudaDiagonalOperator.from_scipy(sps.diags(w).tocsr(), sp)
+    else:
+        M = (sps.random(dim, dim, density=0.1, random_state=1) + sps.eye(dim)).tocsr()
+        W, op = M, CudaCsrOperator(M, sp)
+    emu.calls.clear()
+    np.testing.assert_allclose(op.apply2(VA, VB), O.inner(A, B, W), atol=1e-13)
+    np.testing.assert_allclose(VA.gramian(op), O.gramian(A, W), atol=1e-13)
+    np.testing.assert_allclose(VA[1:5].inner(VA, op), O.inner(A[:, 1:5], A, W), atol=1e-13)
+    np.testing.assert_allclose(VA[:4].pairwise_inner(VB, op), O.pairwise_inner(A[:, :4], B, W), atol=1e-13)
+    np.testing.assert_allclose(VA.norm(op), O.norm(A, W), atol=1e-13)
+    np.testing.assert_allclose(op.apply(VB).to_numpy(), O.apply_product(W, B), atol=1e-14)
+    WT = W if kind == 'diag' else W.T
+    np.testing.assert_allclose(op.apply_adjoint(VB).to_numpy(), O.apply_product(WT, B), atol=1e-14)
+    if kind == 'diag':       # fused: only the two explicit apply() calls ever produce W·U
+        assert emu.calls.count('pmc_diag_apply') == 2
+    else:
+        assert emu.calls.count('pmc_csr_gram') == 3
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
+def test_standalone_gram_schmidt_golden(emu, name):
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('gram_schmidt')
+    sp = space_of(g['A'].shape[0])
+    prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp),
+            'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
+    VA = sp.from_numpy(g['A'])
+    Q, R = alg.gram_schmidt(VA, product=prod, return_R=True)
+    np.testing.assert_array_equal(VA.to_numpy(), g['A'])        # copy=True leaves the input alone
+    np.testing.assert_allclose(Q.to_numpy(), g[f'Q_{name}'], atol=1e-11)
+    np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
+    Q0 = alg.gram_schmidt(sp.from_numpy(g['A'][:, :4]))
+    Q0.append(sp.from_numpy(g['A'][:, 10:]))
+    if name == 'euclid':
+        Q1 = alg.gram_schmidt(Q0, offset=4, copy=False)
+        assert Q1 is Q0
+        np.testing.assert_allclose(Q1.to_numpy(), g['Q_offset'], atol=1e-11)
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
+def test_standalone_pod_golden(emu, name):
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('pod')
+    sp = space_of(g['A'].shape[0])
+    W = {'euclid': None, 'diag': g['w'], 'csr': csr_from(g, 'M')}[name]
+    prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp),
+            'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
+    VA = sp.from_numpy(g['A'])
+    U, s, Vh = alg.method_of_snapshots(VA, product=prod)
+    np.testing.assert_allclose(s, g[f'mos_s_{name}'], rtol=1e-10)
+    assert O.subspace_angle(g[f'mos_U_{name}'], U.to_numpy(), W) < 1e-8
+    U, s, _ = alg.qr_svd(VA, product=prod)
+    np.testing.assert_allclose(s, g[f'qr_s_{name}'], rtol=1e-10)
+    assert O.subspace_angle(g[f'qr_U_{name}'], U.to_numpy(), W) < 1e-8
+    U, s = alg.pod(VA, product=prod, modes=10, method='method_of_snapshots')
+    np.testing.assert_allclose(s, g[f'pod_s_{name}'], rtol=1e-10)
+    assert len(U) == 10 and O.subspace_angle(g[f'pod_U_{name}'], U.to_numpy(), W) < 1e-8
+    if name == 'euclid':
+        U, s = alg.pod(sp.from_numpy(g['A_illcond']), rtol=1e-7, method='method_of_snapshots')
+        # method_of_snapshots squares the condition number: eigenvalues carry an absolute error of
+        # eps * lambda_max, so the small singular values are only comparable through s**2
+        np.testing.assert_allclose(s ** 2, g['pod_s_illcond'] ** 2, rtol=1e-9, atol=1e-13)
+        assert O.orthogonality_error(U.to_numpy()) < 1e-10
+
+
+def test_standalone_project_golden(emu):
+    from pymor_b200.operators import CudaCsrOperator
+    g = load_golden('projection')
+    sp = space_of(g['V'].shape[0])
+    op, prod = CudaCsrOperator(csr_from(g, 'Mop'), sp), CudaCsrOperator(csr_from(g, 'P'), sp)
+    V, U = sp.from_numpy(g['V']), sp.from_numpy(g['U'])
+    np.testing.assert_allclose(alg.project(op, V, U), g['proj_both'], atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, V, U, product=prod), g['proj_both_product'], atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, U, U), g['proj_galerkin'], atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, None, U).to_numpy(), g['proj_source_only'], atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, V, None).inner(U), g['proj_range_only'], atol=1e-12)
+    np.testing.assert_allclose(op.pairwise_apply2(V, U[:len(V)]), g['pairwise_apply2'], atol=1e-12)
+
+
+def test_thermalblock_golden(emu):
+    """Config 1 in miniature through the stand-alone drivers."""
+    from pymor_b200.operators import CudaCsrOperator
+    g = load_golden('thermalblock')
+    S, P = g['snapshots'], csr_from(g, 'P')
+    sp = space_of(S.shape[0])
+    prod = CudaCsrOperator(P, sp)
+    snaps = sp.empty(reserve=S.shape[1])
+    for i in range(S.shape[1]):                      # appended one solve at a time like reduce_pod
+        snaps.append(sp.from_numpy(S[:, [i]]))
+    basis, svals = alg.pod(snaps, modes=5, product=prod)
+    np.testing.assert_allclose(svals, g['pod_qr_s'], rtol=1e-10)
+    assert O.subspace_angle(g['pod_qr_U'], basis.to_numpy(), P) < 1e-8
+    basis2, svals2 = alg.pod(snaps, modes=5, product=prod, method='method_of_snapshots')
+    np.testing.assert_allclose(svals2, g['pod_mos_s'], rtol=1e-10)
+    B = sp.from_numpy(g['pod_qr_U'])
+    for i in range(int(g['n_ops'])):
+        n = len(g[f'op{i}_indptr']) - 1
+        Mi = sps.csr_matrix((g[f'op{i}_data'], g[f'op{i}_indices'], g[f'op{i}_indptr']), shape=(n, n))
+        np.testing.assert_allclose(alg.project(CudaCsrOperator(Mi, sp), B, B), g[f'op{i}_proj'], atol=1e-12)
+
+
+def test_dlpack_roundtrip(emu, rng):
+    import torch
+    sp = space_of(32)
+    t = torch.from_numpy(rng.standard_normal((5, 32)))
+    V = sp.make_array(t)
+    assert V.impl._buf.data_ptr() == t.data_ptr()          # zero-copy adoption
+    np.testing.assert_array_equal(V.to_numpy(), t.numpy().T)
+    back = torch.from_dlpack(V)
+    assert back.data_ptr() == t.data_ptr() and back.shape == (5, 32)
+    odd = torch.from_numpy(rng.standard_normal((3, 33)))[:, :32]   # odd row stride: copied
+    W = sp.make_array(odd)
+    assert W.impl._buf.data_ptr() != odd.data_ptr()
+    np.testing.assert_array_equal(W.to_numpy(), odd.numpy().T)
+
+
+# --------------------------------------------------------------------------------------------
+# with the reference present: its own test-suite and its own algorithms on CudaVectorArray
+# --------------------------------------------------------------------------------------------
+def _run(script, *args):
+    return subprocess.run([sys.executable, str(ROOT / 'tests' / 'reference_contract' / script), *args],
+                          capture_output=True, text=True, timeout=3000)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REFERENCE, reason='reference not present')
+def test_reference_contract_suite_on_cuda_backend():
+    """pymortests/vectorarray.py + algorithms/{gram_schmidt,svd_va,pod}.py with backend 'cuda'.
+    The only deselected test multiplies by 1j (complex is out of scope by design)."""
+    r = _run('run_contract.py', 'src/pymortests/vectorarray.py', 'src/pymortests/algorithms/gram_schmidt.py',
+             'src/pymortests/algorithms/svd_va.py', 'src/pymortests/algorithms/pod.py',
+             '--deselect', 'src/pymortests/vectorarray.py::test_scal_imaginary')
+    tail = r.stdout[-3000:]
+    assert r.returncode == 0, tail
+    assert ' passed' in tail and 'failed' not in tail
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REFERENCE, reason='reference not present')
+def test_pymor_algorithms_run_unchanged():
+    r = _run('run_contract.py', str(ROOT / 'tests' / 'reference_contract' / 'pymor_mode_checks.py'))
+    tail = r.stdout[-3000:]
+    assert r.returncode == 0, tail
