@@ -560,6 +560,21 @@ class CudaVectorSpace(VectorSpace):
             impl._buf[:count, :self._local_dim].copy_(torch.from_numpy(rows))
         return CudaVectorArray(self, impl)
 
+    def from_local_numpy(self, shard, reserve=0):
+        """Upload THIS RANK's rows: ``shard`` has shape ``(local_dim, len)``.  A Fortran-ordered
+        shard (one vector per contiguous column) in pinned memory is copied by a single DMA."""
+        shard = np.asarray(shard)
+        if np.iscomplexobj(shard):
+            raise NotImplementedError('CudaVectorArray is real fp64; complex data is not supported')
+        assert shard.ndim == 2 and shard.shape[0] == self._local_dim
+        count = shard.shape[1]
+        impl = CudaVectorArrayImpl.allocate(self, count, reserve)
+        if count and self._local_dim:
+            rows = shard.T if shard.T.flags.c_contiguous and shard.dtype == np.float64 \
+                else np.ascontiguousarray(shard.T, dtype=np.float64)
+            impl._buf[:count, :self._local_dim].copy_(torch.from_numpy(rows), non_blocking=True)
+        return CudaVectorArray(self, impl)
+
     def from_numpy(self, data, ensure_copy=False):
         """``data`` is the GLOBAL ``(dim, len)`` array; always copies (host -> device)."""
         return self._upload(data)

@@ -1,0 +1,314 @@
+"""Parity of the CUDA path (through the C ABI, real kernels) with the CPU oracle and the golden
+fixtures produced by the reference.  All tests here need a B200 (``-m gpu``).
+
+Tolerances (north star): Gram and lincomb entries relative 1e-12 (relative to ||a_i|| ||b_j|| resp.
+||A[d,:]|| ||c_j||), singular values relative 1e-10, subspace angles < 1e-8,
+orthogonality error no worse than the reference's.  Index / byte work (amax indices, dofs, copies) is
+bit-exact.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from conftest import csr_from, load_golden
+from oracle import numpy_path as O
+
+pytestmark = pytest.mark.gpu
+
+GRAM_TOL = 1e-12
+LINCOMB_TOL = 1e-12
+
+
+@pytest.fixture(scope='module')
+def loaded_lib():
+    """The product path must be the native library, loaded from the tree."""
+    from pymor_b200 import _lib
+    _lib.set_library_for_testing(None)
+    lib = _lib.load_library()
+    assert 'libpymor_b200.so' in str(lib._name)
+    return lib
+
+
+def space_of(dim):
+    from pymor_b200.vectorarray import CudaVectorSpace
+    return CudaVectorSpace(dim)
+
+
+def test_all_symbols_and_fp64_peak(loaded_lib):
+    from pymor_b200 import _lib
+    for name in _lib.EXPORTED_SYMBOLS:
+        assert hasattr(loaded_lib, name)
+    ctx = _lib.get_context('cuda')
+    assert ctx.sm_count >= 100
+    dmma = ctx.measure_fp64_peak(True, 50.0)
+    dfma = ctx.measure_fp64_peak(False, 50.0)
+    print(f'FP64 peak: DMMA {dmma:.1f} TFLOP/s, DFMA {dfma:.1f} TFLOP/s')
+    assert dmma > 5 and dfma > 5
+
+
+# (dim, kA, kB): edge sizes, ragged tiles, k below / at / above the 128 tile, n not a multiple of 16
+SHAPES = [(1, 1, 1), (15, 3, 2), (16, 16, 16), (1000, 17, 130), (4099, 128, 128), (5000, 129, 257),
+          (33333, 200, 64), (70001, 500, 500)]
+
+
+@pytest.mark.parametrize('dim,ka,kb', SHAPES)
+@pytest.mark.parametrize('weighted', [False, True])
+def test_gram_parity(loaded_lib, rng, dim, ka, kb, weighted):
+    sp = space_of(dim)
+    A, B = rng.standard_normal((dim, ka)), rng.standard_normal((dim, kb))
+    VA, VB = sp.from_numpy(A), sp.from_numpy(B)
+    w = rng.uniform(0.5, 1.5, dim) if weighted else None
+    prod = None
+    if weighted:
+        from pymor_b200.operators import CudaDiagonalOperator
+        prod = CudaDiagonalOperator(w, sp)
+    for generic in (False, True):                       # TMA+DMMA path and the generic kernel
+        sp.force_generic_kernels(generic)
+        G = VA.inner(VB, prod)
+        assert G.shape == (ka, kb) and G.flags.f_contiguous
+        assert O.gram_rel_error(G, O.inner(A, B, w), A, B, w) < GRAM_TOL
+        S = VA.gramian(prod)
+        assert O.gram_rel_error(S, O.gramian(A, w), A, A, w) < GRAM_TOL
+        np.testing.assert_array_equal(S, S.T)           # bitwise symmetric like the reference's dsyrk
+        S2 = VA.gramian(prod)
+        np.testing.assert_array_equal(S, S2)            # fixed summation order: reproducible
+        # same buffer, different columns = plain GEMM (gram_schmidt's check)
+        off = ka // 3
+        G2 = VA[off:].inner(VA, prod)
+        assert O.gram_rel_error(G2, O.inner(A[:, off:], A, w), A[:, off:], A, w) < GRAM_TOL
+    sp.force_generic_kernels(False)
+
+
+@pytest.mark.parametrize('dim,k,m', [(1, 1, 1), (17, 5, 3), (16, 4, 16), (1000, 130, 17), (4099, 128, 128),
+                                     (5000, 257, 129), (33333, 64, 200), (70001, 300, 300)])
+def test_lincomb_parity(loaded_lib, rng, dim, k, m):
+    sp = space_of(dim)
+    A, C = rng.standard_normal((dim, k)), rng.standard_normal((k, m))
+    VA = sp.from_numpy(A)
+    ref = O.lincomb(A, C)
+    for generic in (False, True):
+        sp.force_generic_kernels(generic)
+        R = VA.lincomb(C).to_numpy()
+        assert O.lincomb_rel_error(R, ref, A, C) < LINCOMB_TOL
+        R2 = VA[::2].lincomb(C[::2]).to_numpy()          # strided view (TMA stride = 2 columns)
+        assert O.lincomb_rel_error(R2, O.lincomb(A[:, ::2], C[::2]), A[:, ::2], C[::2]) < LINCOMB_TOL
+    sp.force_generic_kernels(False)
+
+
+@pytest.mark.parametrize('dim', [1, 2, 3, 2047, 2048, 2049, 100003, 3000001])
+def test_streaming_kernels_parity(loaded_lib, rng, dim):
+    from pymor_b200.operators import CudaDiagonalOperator
+    sp = space_of(dim)
+    k = 5 if dim < 1000000 else 2
+    A, B = rng.standard_normal((dim, k)), rng.standard_normal((dim, k))
+    w = rng.uniform(0.5, 1.5, dim)
+    VA, VB, prod = sp.from_numpy(A), sp.from_numpy(B), CudaDiagonalOperator(w, sp)
+    scale = np.sqrt(dim)
+    np.testing.assert_allclose(VA.pairwise_inner(VB), O.pairwise_inner(A, B), atol=1e-13 * dim, rtol=1e-13)
+    np.testing.assert_allclose(VA.pairwise_inner(VB, prod), O.pairwise_inner(A, B, w), atol=1e-13 * dim, rtol=1e-13)
+    np.testing.assert_allclose(VA.norm2(), O.norm2(A), rtol=1e-13)
+    np.testing.assert_allclose(VA.norm(prod), O.norm(A, w), rtol=1e-13)
+    np.testing.assert_allclose(VA[1].pairwise_inner(VB[0]), O.pairwise_inner(A[:, [1]], B[:, [0]]),
+                               atol=1e-13 * dim)
+    al = rng.standard_normal(k)
+    Y = VA.copy(); Y.axpy(al, VB)
+    np.testing.assert_allclose(Y.to_numpy(), A + B * al, rtol=0, atol=1e-15 * scale)
+    Y = VA.copy(); Y.axpy(-0.75, VB[0])
+    np.testing.assert_allclose(Y.to_numpy(), A - 0.75 * B[:, [0]], rtol=0, atol=1e-15 * scale)
+    Y = VA.copy(); Y[::-1].scal(al)
+    np.testing.assert_array_equal(Y.to_numpy(), A * al[::-1])
+    np.testing.assert_array_equal(VA[[k - 1, 0, 0]].copy().to_numpy(), A[:, [k - 1, 0, 0]])
+    np.testing.assert_array_equal(prod.apply(VA).to_numpy(), w[:, None] * A)
+    idx, val = VA.amax()
+    oi, ov = O.amax(A)
+    np.testing.assert_array_equal(idx, oi)
+    np.testing.assert_array_equal(val, ov)
+    dofs = [0, dim - 1, dim // 2, dim // 2]
+    np.testing.assert_array_equal(VA.dofs(dofs), O.dofs(A, dofs))
+
+
+def test_amax_ties_first_index(loaded_lib):
+    sp = space_of(5000)
+    A = np.zeros((5000, 3))
+    A[[7, 4000], 0] = [-2.0, 2.0]       # tie: first index wins
+    A[4999, 1] = 1.0
+    VA = sp.from_numpy(A)
+    idx, val = VA.amax()
+    np.testing.assert_array_equal(idx, [7, 4999, 0])
+    np.testing.assert_array_equal(val, [2.0, 1.0, 0.0])
+
+
+def test_misaligned_dlpack_views_take_generic_path(loaded_lib, rng):
+    """Odd leading dimension / misaligned base: every kernel must still be correct."""
+    import torch
+    dim, k = 1000, 6
+    host = rng.standard_normal((k, dim + 1))
+    t = torch.from_numpy(host).cuda()[:, 1:]          # base misaligned by 8 bytes, ld odd
+    from pymor_b200.vectorarray import CudaVectorArray, CudaVectorArrayImpl
+    sp = space_of(dim)
+    V = CudaVectorArray(sp, CudaVectorArrayImpl(sp, t, k))     # force adoption without the alignment check
+    A = host[:, 1:].T
+    assert O.gram_rel_error(V.gramian(), O.gramian(A), A, A) < GRAM_TOL
+    np.testing.assert_allclose(V.norm2(), O.norm2(A), rtol=1e-13)
+    C = rng.standard_normal((k, 20))
+    assert O.lincomb_rel_error(V.lincomb(C).to_numpy(), O.lincomb(A, C), A, C) < LINCOMB_TOL
+    Y = V.copy(); Y.axpy(2.0, V[::-1])
+    np.testing.assert_allclose(Y.to_numpy(), A + 2 * A[:, ::-1], atol=1e-14)
+
+
+def test_vecops_golden(loaded_lib):
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('vecops')
+    A, B, C, alpha = g['A'], g['B'], g['C'], g['alpha']
+    sp = space_of(A.shape[0])
+    VA, VB = sp.from_numpy(A), sp.from_numpy(B)
+    Wd, Wm = CudaDiagonalOperator(g['w'], sp), CudaCsrOperator(csr_from(g, 'M'), sp)
+    tight = dict(rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(VA.inner(VB), g['inner'], **tight)
+    np.testing.assert_allclose(VA.inner(VB, Wd), g['inner_diag'], **tight)
+    np.testing.assert_allclose(VA.inner(VB, Wm), g['inner_csr'], **tight)
+    np.testing.assert_allclose(VA.gramian(), g['gramian'], **tight)
+    np.testing.assert_allclose(VA.gramian(Wd), g['gramian_diag'], **tight)
+    np.testing.assert_allclose(VA.gramian(Wm), g['gramian_csr'], **tight)
+    lb = B.shape[1]
+    np.testing.assert_allclose(VA[:lb].pairwise_inner(VB), g['pairwise'], **tight)
+    np.testing.assert_allclose(VA[:lb].pairwise_inner(VB, Wd), g['pairwise_diag'], **tight)
+    np.testing.assert_allclose(VA[:lb].pairwise_inner(VB, Wm), g['pairwise_csr'], **tight)
+    np.testing.assert_allclose(VA.lincomb(C).to_numpy(), g['lincomb'], **tight)
+    np.testing.assert_allclose(VA.norm(), g['norm'], **tight)
+    np.testing.assert_allclose(VA.norm(Wd), g['norm_diag'], **tight)
+    np.testing.assert_allclose(VA.norm2(Wm), g['norm2_csr'], **tight)
+    Y = VA.copy(); Y.axpy(0.37, VA[::-1]); np.testing.assert_allclose(Y.to_numpy(), g['axpy_scalar_rev'], **tight)
+    Y = VA.copy(); Y.axpy(alpha, VB[0]); np.testing.assert_allclose(Y.to_numpy(), g['axpy_vec_bcast'], **tight)
+    Y = VA.copy(); Y[[5, 1, 3]].axpy(alpha[:3], VB[[0, 4, 2]]); np.testing.assert_allclose(Y.to_numpy(), g['axpy_list'], **tight)
+    Y = VA.copy(); Y.scal(alpha); np.testing.assert_allclose(Y.to_numpy(), g['scal_vec'], **tight)
+    Y = VA.copy(); Y[1:6:2].scal(-2.5); np.testing.assert_allclose(Y.to_numpy(), g['scal_slice'], **tight)
+    np.testing.assert_array_equal(VA[[6, 0, 2]].dofs(g['dof_idx']), g['dofs'])
+    ai, av = VA.amax()
+    np.testing.assert_array_equal(ai, g['amax_idx'])
+    np.testing.assert_array_equal(av, g['amax_val'])
+    np.testing.assert_allclose(VA[[6, 0, 0, 2]].inner(VB[3:0:-1]), g['view_inner'], **tight)
+    Z = VA.copy(); Z.append(VB[[1, 1, 4]]); del Z[[0, 2]]
+    np.testing.assert_array_equal(Z.to_numpy(), g['append_del'])
+    np.testing.assert_allclose(Wm.apply(VA).to_numpy(), g['apply_csr'], **tight)
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
+def test_gram_schmidt_golden(loaded_lib, name):
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('gram_schmidt')
+    sp = space_of(g['A'].shape[0])
+    W = {'euclid': None, 'diag': g['w'], 'csr': csr_from(g, 'M')}[name]
+    prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp), 'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
+    Q, R = alg.gram_schmidt(sp.from_numpy(g['A']), product=prod, return_R=True)
+    np.testing.assert_allclose(Q.to_numpy(), g[f'Q_{name}'], atol=1e-11)
+    np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
+    # orthogonality error no worse than the reference's (up to a factor for rounding noise)
+    assert O.orthogonality_error(Q.to_numpy(), W) <= max(4 * O.orthogonality_error(g[f'Q_{name}'], W), 1e-14)
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
+def test_pod_golden(loaded_lib, name):
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('pod')
+    sp = space_of(g['A'].shape[0])
+    W = {'euclid': None, 'diag': g['w'], 'csr': csr_from(g, 'M')}[name]
+    prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp), 'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
+    VA = sp.from_numpy(g['A'])
+    U, s, Vh = alg.method_of_snapshots(VA, product=prod)
+    np.testing.assert_allclose(s, g[f'mos_s_{name}'], rtol=1e-10)
+    assert O.subspace_angle(g[f'mos_U_{name}'], U.to_numpy(), W) < 1e-8
+    U, s, _ = alg.qr_svd(VA, product=prod)
+    np.testing.assert_allclose(s, g[f'qr_s_{name}'], rtol=1e-10)
+    assert O.subspace_angle(g[f'qr_U_{name}'], U.to_numpy(), W) < 1e-8
+    U, s = alg.pod(VA, product=prod, modes=10, method='method_of_snapshots')
+    np.testing.assert_allclose(s, g[f'pod_s_{name}'], rtol=1e-10)
+    assert O.subspace_angle(g[f'pod_U_{name}'], U.to_numpy(), W) < 1e-8
+    assert O.orthogonality_error(U.to_numpy(), W) <= max(4 * O.orthogonality_error(g[f'pod_U_{name}'], W), 1e-13)
+
+
+def test_projection_and_thermalblock_golden(loaded_lib):
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaCsrOperator
+    g = load_golden('projection')
+    sp = space_of(g['V'].shape[0])
+    op, prod = CudaCsrOperator(csr_from(g, 'Mop'), sp), CudaCsrOperator(csr_from(g, 'P'), sp)
+    V, U = sp.from_numpy(g['V']), sp.from_numpy(g['U'])
+    np.testing.assert_allclose(alg.project(op, V, U), g['proj_both'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, V, U, product=prod), g['proj_both_product'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, U, U), g['proj_galerkin'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, None, U).to_numpy(), g['proj_source_only'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, V, None).inner(U), g['proj_range_only'], rtol=1e-12, atol=1e-12)
+    t = load_golden('thermalblock')
+    S, P = t['snapshots'], csr_from(t, 'P')
+    sp = space_of(S.shape[0])
+    prod = CudaCsrOperator(P, sp)
+    basis, svals = alg.pod(sp.from_numpy(S), modes=5, product=prod)
+    np.testing.assert_allclose(svals, t['pod_qr_s'], rtol=1e-10)
+    assert O.subspace_angle(t['pod_qr_U'], basis.to_numpy(), P) < 1e-8
+    basis2, svals2 = alg.pod(sp.from_numpy(S), modes=5, product=prod, method='method_of_snapshots')
+    np.testing.assert_allclose(svals2, t['pod_mos_s'], rtol=1e-10)
+    B = sp.from_numpy(t['pod_qr_U'])
+    for i in range(int(t['n_ops'])):
+        n = len(t[f'op{i}_indptr']) - 1
+        Mi = sps.csr_matrix((t[f'op{i}_data'], t[f'op{i}_indices'], t[f'op{i}_indptr']), shape=(n, n))
+        np.testing.assert_allclose(alg.project(CudaCsrOperator(Mi, sp), B, B), t[f'op{i}_proj'], rtol=1e-12, atol=1e-12)
+
+
+def test_csr_twoform_multi_panel(loaded_lib, rng):
+    """CSR two-form across several row panels (the fused V^T (M U) path) vs SciPy."""
+    from pymor_b200.operators import CudaCsrOperator
+    dim, kv, ku = 60000, 40, 600          # 600 columns -> ~10k-row panels -> 6 panels
+    M = (sps.diags([-np.ones(dim - 1), 2.5 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1])
+         + sps.random(dim, dim, density=2e-5, random_state=3)).tocsr()
+    sp = space_of(dim)
+    V, U = rng.standard_normal((dim, kv)), rng.standard_normal((dim, ku))
+    op = CudaCsrOperator(M, sp)
+    G = op.apply2(sp.from_numpy(V), sp.from_numpy(U))
+    MU = M @ U
+    assert O.gram_rel_error(G, V.T @ MU, V, MU) < GRAM_TOL
+    np.testing.assert_allclose(op.apply(sp.from_numpy(U[:, :7])).to_numpy(), MU[:, :7], rtol=1e-13, atol=1e-13)
+
+
+def test_full_size_properties(loaded_lib):
+    """Size-independent properties at a BASELINE-scale shape (config 2: 2M DOF x 500 snapshots):
+    linearity of the Gramian, ||A c|| consistency between lincomb and Gramian, POD orthonormality and
+    reconstruction of a known spectrum."""
+    import torch
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaDiagonalOperator
+    n, k = 2_000_000, 500
+    sp = space_of(n)
+    gen = torch.Generator(device='cuda').manual_seed(7)
+    Gn = torch.randn((k, n), generator=gen, device='cuda', dtype=torch.float64) / np.sqrt(n)
+    rng = np.random.default_rng(7)
+    Qk, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    sig = 10.0 ** (-2 * np.arange(k) / (k - 1))
+    base = sp.make_array(Gn)
+    A = base.lincomb(np.diag(sig) @ Qk.T)            # A = Gn diag(sig) Qk^T
+    del base, Gn
+    w = torch.rand(n, generator=gen, device='cuda', dtype=torch.float64) + 0.5
+    prod = CudaDiagonalOperator(w, sp)
+    G = A.gramian(prod)
+    np.testing.assert_array_equal(G, G.T)
+    # Gramian consistency: c^T G c == || A c ||_W^2
+    c = rng.standard_normal((k, 3))
+    Ac = A.lincomb(c)
+    np.testing.assert_allclose(np.einsum('ia,ij,ja->a', c, G, c), Ac.norm2(prod), rtol=1e-11)
+    # scaling linearity: gramian(2A) == 4 gramian(A) exactly (power of two)
+    A2 = A.copy(); A2.scal(2.0)
+    np.testing.assert_array_equal(A2.gramian(prod), 4 * G)
+    del A2, Ac
+    U, s = alg.pod(A, product=prod, method='method_of_snapshots')
+    assert len(U) == k
+    err = np.max(np.abs(U.gramian(prod) - np.eye(k)))
+    assert err < 1e-10, err
+    # the weighted spectrum is close to the prescribed one (random W ~ U(0.5,1.5) has mean 1)
+    assert abs(s[0] / sig[0] - 1) < 0.05 and abs(s[-1] / sig[-1] - 1) < 0.2
+    # reconstruction: A == U (U^T W A)
+    coeff = U.inner(A[:8], prod)
+    R = U.lincomb(coeff)
+    R.axpy(-1.0, A[:8])
+    assert np.max(R.norm(prod) / A[:8].norm(prod)) < 1e-9
