@@ -1,0 +1,106 @@
+"""Worker of tests/test_sharded_gloo.py: one process per rank (gloo, CPU).
+
+Every rank runs the SAME program on its row shard (SPMD) -- the multi-GPU execution model of the
+backend (pymor_b200/dist.py) -- with the C ABI served by the NumPy emulation.  Results are compared
+with the oracle evaluated on the global data, and with the oracle's restatement of the reference's
+gather-and-sum (src/pymor/vectorarrays/mpi.py:394-445).
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import scipy.sparse as sps
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests'))
+
+from emulated_lib import EmulatedLib  # noqa: E402
+from oracle import numpy_path as O  # noqa: E402
+
+from pymor_b200 import _lib, algorithms as alg  # noqa: E402
+from pymor_b200.dist import ProcessGroupComm, partition  # noqa: E402
+from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator  # noqa: E402
+from pymor_b200.vectorarray import CudaVectorSpace  # noqa: E402
+
+
+def main():
+    dist.init_process_group('gloo')
+    _lib.set_library_for_testing(EmulatedLib())
+    comm = ProcessGroupComm()
+    rank, size = comm.rank, comm.size
+    for dim in (1, 5, 103):                      # dim < size: some ranks own zero rows
+        rng = np.random.default_rng(11)          # identical global data on every rank
+        k = 9
+        A = rng.standard_normal((dim, k)) + 2 * rng.standard_normal((dim, 1))
+        B = rng.standard_normal((dim, k))
+        w = rng.uniform(0.5, 1.5, dim)
+        sp = CudaVectorSpace(dim, device='cpu', comm=comm)
+        dims, offs = partition(dim, size)
+        assert sp.local_dim == dims[rank] and sp.offset == offs[rank] and sp.dim == dim
+        VA, VB = sp.from_numpy(A), sp.from_numpy(B)
+        prod = CudaDiagonalOperator(w, sp)
+        lo, hi = offs[rank], offs[rank] + dims[rank]
+
+        # reductions equal the global result and the reference's "sum of local results"
+        G = VA.inner(VB)
+        np.testing.assert_allclose(G, O.inner(A, B), atol=1e-12)
+        parts = [O.inner(A[o:o + d], B[o:o + d]) for o, d in zip(offs, dims)]
+        np.testing.assert_allclose(G, O.sharded_reduce(parts), atol=1e-12)
+        np.testing.assert_allclose(VA.gramian(prod), O.gramian(A, w), atol=1e-12)
+        np.testing.assert_allclose(VA.pairwise_inner(VB, prod), O.pairwise_inner(A, B, w), atol=1e-12)
+        np.testing.assert_allclose(VA.norm(), O.norm(A), atol=1e-12)
+        np.testing.assert_allclose(VA[2:7].norm2(prod), O.norm2(A[:, 2:7], w), atol=1e-12)
+        # no-communication ops act on the shard only
+        Y = VA.copy(); Y.axpy(-0.5, VB); Y.scal(np.arange(k))
+        np.testing.assert_allclose(Y.to_numpy(), (A - 0.5 * B) * np.arange(k), atol=1e-13)
+        np.testing.assert_allclose(Y.to_torch().numpy().T, ((A - 0.5 * B) * np.arange(k))[lo:hi], atol=1e-13)
+        C = rng.standard_normal((k, 4))
+        np.testing.assert_allclose(VA.lincomb(C).to_numpy(), O.lincomb(A, C), atol=1e-12)
+        # dofs: owner lookup + sum (mpi.py:421-432); amax: lowest shard wins ties (mpi.py:341-347)
+        dofs = [0, dim - 1, dim // 2]
+        np.testing.assert_array_equal(VA.dofs(dofs), O.dofs(A, dofs))
+        T = A.copy()
+        T[0, 0], T[dim - 1, 0] = 7.0, -7.0        # tie between first and last shard
+        idx, val = sp.from_numpy(T).amax()
+        oi, ov = O.amax(T)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(val, ov)
+        inds = [O.amax(T[o:o + d])[0] if d else np.zeros(k, dtype=np.int64) for o, d in zip(offs, dims)]
+        vals = [O.amax(T[o:o + d])[1] if d else np.full(k, -1.0) for o, d in zip(offs, dims)]
+        si, sv = O.sharded_amax(inds, vals, offs)
+        np.testing.assert_array_equal(idx, si)
+        np.testing.assert_array_equal(val, sv)
+
+        if dim >= k:
+            # the algorithms take identical control-flow decisions on every rank
+            Q, R = alg.gram_schmidt(VA, product=prod, return_R=True)
+            Qo, Ro = O.gram_schmidt(A, w, return_R=True)
+            np.testing.assert_allclose(R, Ro, atol=1e-11)
+            np.testing.assert_allclose(Q.to_numpy(), Qo, atol=1e-11)
+            U, s = alg.pod(VA, product=prod, method='method_of_snapshots')
+            Uo, so = O.pod(A, w)
+            np.testing.assert_allclose(s, so, rtol=1e-10)
+            assert O.subspace_angle(Uo, U.to_numpy(), w) < 1e-8
+            # block-diagonal CSR operator (no halo): two-form and projection
+            blocks = [sps.random(int(d), int(d), density=0.3, random_state=3 + i) + sps.eye(int(d)) for i, d in enumerate(dims)]
+            M = sps.block_diag(blocks).tocsr()
+            op = CudaCsrOperator(M, sp)
+            np.testing.assert_allclose(alg.project(op, VA, VB), O.project(M, A, B), atol=1e-11)
+    # a CSR operator coupling rows of different shards needs a halo exchange: refuse loudly
+    if size > 1:
+        sp = CudaVectorSpace(10, device='cpu', comm=comm)
+        M = sps.diags([np.ones(9), 2 * np.ones(10), np.ones(9)], [-1, 0, 1]).tocsr()
+        try:
+            CudaCsrOperator(M, sp)
+            raise SystemExit('expected NotImplementedError')
+        except NotImplementedError:
+            pass
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f'rank {rank}: ok')
+
+
+if __name__ == '__main__':
+    main()

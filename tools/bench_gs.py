@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Config 3 of BASELINE.json: re-iterated Gram-Schmidt of k vectors with a diagonal mass-matrix
+product (HBM-bound: one weighted dot + one axpy per pair-step, a host sync after every dot).
+
+Input family of SURVEY.md §8d: a_i = g_i + 2 s  =>  every vector i >= 1 re-iterates exactly once,
+i.e. k(k-1) pair-steps, which makes the byte model exact:
+  per pair-step 24 n (weighted dot: a_j, a_i, w) + 24 n (axpy: read a_j, a_i, write a_i)
+  per vector    3 weighted norms (16 n each) + 1 scal (16 n);  plus the final check Gramian.
+Prints one JSON line (not the driver's bench contract; results are quoted in DESIGN.md).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
+import numpy as np  # noqa: E402
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=10_000_000)
+    ap.add_argument('--k', type=int, default=256)
+    ap.add_argument('--cpu-n', type=int, default=0, help='also time the oracle on this many rows')
+    args = ap.parse_args()
+    import torch
+
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaDiagonalOperator
+    from pymor_b200.vectorarray import CudaVectorArrayImpl, CudaVectorSpace
+    n, k = args.n, args.k
+    space = CudaVectorSpace(n)
+    A = space.random_device(k, seed=1, scale=1.0 / np.sqrt(n))
+    s = space.random_device(1, seed=2, scale=1.0 / np.sqrt(n))
+    A.axpy(2.0, s)
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    w = torch.rand(n, generator=gen, device='cuda', dtype=torch.float64) + 0.5
+    prod = CudaDiagonalOperator(w, space)
+
+    counts = {'pairwise_inner': 0, 'axpy': 0, 'scal': 0}
+    for name in counts:
+        orig = getattr(CudaVectorArrayImpl, name)
+
+        def wrapped(self, *a, _orig=orig, _name=name, **kw):
+            counts[_name] += 1
+            return _orig(self, *a, **kw)
+        setattr(CudaVectorArrayImpl, name, wrapped)
+
+    # warm up the kernels on a small slice
+    alg.gram_schmidt(A[:8], product=prod)
+    for c in counts:
+        counts[c] = 0
+    torch.cuda.synchronize()
+    l0 = space.ctx.launch_count
+    t0 = time.perf_counter()
+    Q, R = alg.gram_schmidt(A, product=prod, return_R=True, copy=False, check=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = space.ctx.launch_count - l0
+    pair_steps = counts['axpy']
+    norms = counts['pairwise_inner'] - pair_steps
+    nbytes = pair_steps * 48.0 * n + norms * 16.0 * n + counts['scal'] * 16.0 * n
+    err = float(np.max(np.abs(Q.gramian(prod) - np.eye(len(Q)))))
+    peaks = ROOT / 'MEASURED_PEAKS.json'
+    hbm = json.loads(peaks.read_text())['hbm_gbs'] if peaks.exists() else 6650.0
+    out = {'workload': f'gram_schmidt {n} x {k}, diag-W, re-iterated', 'seconds': dt, 'pair_steps': pair_steps,
+           'weighted_norms': norms, 'scals': counts['scal'], 'algorithmic_bytes': nbytes,
+           'achieved_gbs': nbytes / dt * 1e-9, 'hbm_peak_gbs': hbm,
+           'peak_source': 'MEASURED_PEAKS.json' if peaks.exists() else 'fallback 6650 GB/s',
+           'frac': nbytes / dt * 1e-9 / hbm, 'us_per_pair_step': dt / max(pair_steps, 1) * 1e6,
+           'gpu_launches': launches, 'orth_err': err, 'len_Q': len(Q)}
+    if args.cpu_n:
+        from oracle import numpy_path as O
+        rng = np.random.default_rng(1)
+        Ah = rng.standard_normal((args.cpu_n, k)) / np.sqrt(args.cpu_n) + 2 * rng.standard_normal((args.cpu_n, 1)) / np.sqrt(args.cpu_n)
+        wh = rng.uniform(0.5, 1.5, args.cpu_n)
+        st = {}
+        t0 = time.perf_counter()
+        O.gram_schmidt(Ah, wh, check=False, stats=st)
+        tc = time.perf_counter() - t0
+        out['cpu_baseline'] = {'rows': args.cpu_n, 'seconds': tc, 'pair_steps': st['pair_steps'], 'kind': 'port',
+                               'cores': os.cpu_count(), 'extrapolated_seconds_full_n': tc * n / args.cpu_n}
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
