@@ -63,12 +63,11 @@ reduce_cols_kernel(const double *__restrict__ A, int64_t csA, const double *__re
             }
         } else {
             const int64_t end = (base + CHUNK < n) ? base + CHUNK : n;
-            int u = 0;
-            for (int64_t i = base + threadIdx.x; i < end; i += TPB, u = (u + 1) & (UNROLL - 1)) {
+            for (int64_t i = base + threadIdx.x; i < end; i += TPB) {
                 double x = a[i];
                 double y = NORM ? x : b[i];
                 if (WEIGHTED) y *= w[i];
-                acc[u] = fma(x, y, acc[u]);
+                acc[0] = fma(x, y, acc[0]);
             }
         }
     }

@@ -26,17 +26,29 @@ from pymor_b200.vectorarray import CudaVectorSpace  # noqa: E402
 
 
 def main():
-    dist.init_process_group('gloo')
-    _lib.set_library_for_testing(EmulatedLib())
+    real = '--real' in sys.argv          # real kernels + NCCL, one GPU per rank (tests/test_gpu_multi.py)
+    if real:
+        import os
+
+        import torch
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        device = f'cuda:{local}'
+        dist.init_process_group('nccl', device_id=torch.device(device))
+        _lib.set_library_for_testing(None)
+    else:
+        device = 'cpu'
+        dist.init_process_group('gloo')
+        _lib.set_library_for_testing(EmulatedLib())
     comm = ProcessGroupComm()
     rank, size = comm.rank, comm.size
-    for dim in (1, 5, 103):                      # dim < size: some ranks own zero rows
+    for dim in (1, 5, 103) + ((40013,) if real else ()):    # dim < size: some ranks own zero rows
         rng = np.random.default_rng(11)          # identical global data on every rank
         k = 9
         A = rng.standard_normal((dim, k)) + 2 * rng.standard_normal((dim, 1))
         B = rng.standard_normal((dim, k))
         w = rng.uniform(0.5, 1.5, dim)
-        sp = CudaVectorSpace(dim, device='cpu', comm=comm)
+        sp = CudaVectorSpace(dim, device=device, comm=comm)
         dims, offs = partition(dim, size)
         assert sp.local_dim == dims[rank] and sp.offset == offs[rank] and sp.dim == dim
         VA, VB = sp.from_numpy(A), sp.from_numpy(B)
@@ -55,7 +67,7 @@ def main():
         # no-communication ops act on the shard only
         Y = VA.copy(); Y.axpy(-0.5, VB); Y.scal(np.arange(k))
         np.testing.assert_allclose(Y.to_numpy(), (A - 0.5 * B) * np.arange(k), atol=1e-13)
-        np.testing.assert_allclose(Y.to_torch().numpy().T, ((A - 0.5 * B) * np.arange(k))[lo:hi], atol=1e-13)
+        np.testing.assert_allclose(Y.to_torch().cpu().numpy().T, ((A - 0.5 * B) * np.arange(k))[lo:hi], atol=1e-13)
         C = rng.standard_normal((k, 4))
         np.testing.assert_allclose(VA.lincomb(C).to_numpy(), O.lincomb(A, C), atol=1e-12)
         # dofs: owner lookup + sum (mpi.py:421-432); amax: lowest shard wins ties (mpi.py:341-347)
@@ -84,13 +96,14 @@ def main():
             np.testing.assert_allclose(s, so, rtol=1e-10)
             assert O.subspace_angle(Uo, U.to_numpy(), w) < 1e-8
             # block-diagonal CSR operator (no halo): two-form and projection
-            blocks = [sps.random(int(d), int(d), density=0.3, random_state=3 + i) + sps.eye(int(d)) for i, d in enumerate(dims)]
+            blocks = [sps.random(int(d), int(d), density=min(0.3, 20.0 / max(int(d), 1)), random_state=3 + i)
+                      + sps.eye(int(d)) for i, d in enumerate(dims)]
             M = sps.block_diag(blocks).tocsr()
             op = CudaCsrOperator(M, sp)
             np.testing.assert_allclose(alg.project(op, VA, VB), O.project(M, A, B), atol=1e-11)
     # a CSR operator coupling rows of different shards needs a halo exchange: refuse loudly
     if size > 1:
-        sp = CudaVectorSpace(10, device='cpu', comm=comm)
+        sp = CudaVectorSpace(10, device=device, comm=comm)
         M = sps.diags([np.ones(9), 2 * np.ones(10), np.ones(9)], [-1, 0, 1]).tocsr()
         try:
             CudaCsrOperator(M, sp)

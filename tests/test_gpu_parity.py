@@ -202,8 +202,16 @@ def test_gram_schmidt_golden(loaded_lib, name):
     W = {'euclid': None, 'diag': g['w'], 'csr': csr_from(g, 'M')}[name]
     prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp), 'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
     Q, R = alg.gram_schmidt(sp.from_numpy(g['A']), product=prod, return_R=True)
-    np.testing.assert_allclose(Q.to_numpy(), g[f'Q_{name}'], atol=1e-11)
+    Qh, Qref = Q.to_numpy(), g[f'Q_{name}']
+    assert Qh.shape == Qref.shape                          # the same vectors were removed
     np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
+    # Column 4 of the input is column 1 plus 1e-9 noise: its orthogonalised direction is the
+    # normalised O(1e-9) remainder, i.e. conditioned like 1e9 * eps w.r.t. ANY change of summation
+    # order (the reference itself moves by that much between BLAS builds).  All other columns: 1e-11.
+    others = [c for c in range(Qh.shape[1]) if c != 4]
+    np.testing.assert_allclose(Qh[:, others], Qref[:, others], atol=1e-11)
+    np.testing.assert_allclose(Qh[:, 4], Qref[:, 4], atol=1e-6)
+    np.testing.assert_allclose(Qh @ R, g['A'], atol=1e-12)     # A = Q R holds to rounding (removed columns too)
     # orthogonality error no worse than the reference's (up to a factor for rounding noise)
     assert O.orthogonality_error(Q.to_numpy(), W) <= max(4 * O.orthogonality_error(g[f'Q_{name}'], W), 1e-14)
 
