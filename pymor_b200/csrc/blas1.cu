@@ -11,6 +11,7 @@ constexpr int UNROLL = 4;         // independent 128-bit loads in flight per ope
 constexpr int CHUNK = TPB * 2 * UNROLL;  // rows per block-iteration (2048)
 constexpr int MAX_COLS_PER_LAUNCH = 4096;
 constexpr int PACK = 256;         // scalars / indices carried in kernel parameters per launch
+constexpr int64_t L2_KEEP_BYTES = 96ll << 20;  // single vectors up to this size are kept L2-resident
 
 struct AlphaPack { double v[PACK]; };
 struct IndexPack { int64_t v[PACK]; };
@@ -34,11 +35,14 @@ __global__ void __launch_bounds__(TPB)
 reduce_cols_kernel(const double *__restrict__ A, int64_t csA, const double *__restrict__ B,
                    int64_t csB, const double *__restrict__ w, int64_t n,
                    double *__restrict__ partials, unsigned int *__restrict__ tickets,
-                   double *__restrict__ out) {
+                   double *__restrict__ out, int keep) {
     const int c = blockIdx.y;
     const int bx = gridDim.x;
     const double *a = A + (int64_t)c * csA;
     const double *b = NORM ? a : B + (int64_t)c * csB;
+    // keep: the last operand (the vector being worked on) stays in L2, the others stream past it
+    const uint64_t pol_hot = l2_policy(keep ? 2 : 0), pol_cold = l2_policy(keep ? 1 : 0);
+    const uint64_t pol_a = NORM ? pol_hot : pol_cold;
     double acc[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) acc[u] = 0.0;
@@ -49,9 +53,9 @@ reduce_cols_kernel(const double *__restrict__ A, int64_t csA, const double *__re
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int64_t i = base + 2 * (threadIdx.x + u * TPB);
-                av[u] = ld_stream2(a + i);
-                if (!NORM) bv[u] = ld_stream2(b + i);
-                if (WEIGHTED) wv[u] = ld_stream2(w + i);
+                av[u] = ld_hint2_nc(a + i, pol_a);
+                if (!NORM) bv[u] = ld_hint2_nc(b + i, pol_hot);
+                if (WEIGHTED) wv[u] = ld_hint2_nc(w + i, pol_cold);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -118,11 +122,12 @@ int launch_reduce(pmc_ctx *ctx, const double *A, int64_t csA, const double *B, i
         const double *a = A + (int64_t)c0 * csA;
         const double *b = NORM ? nullptr : B + (int64_t)c0 * csB;
         bool vec = vec_ok(a, csA) && (NORM || vec_ok(b, csB)) && vec_ok(w, 0);
+        const int keep = (ctx->l2_keep && k == 1 && n * 8 <= L2_KEEP_BYTES) ? 1 : 0;
         dim3 grid(bx, kc);
 #define PMC_LAUNCH_RED(WT, VC)                                                                   \
     reduce_cols_kernel<NORM, WT, VC><<<grid, TPB, 0, ctx->stream>>>(a, csA, b, csB, w, n,          \
                                                                    partials_buf, ctx->tickets,    \
-                                                                   out + c0)
+                                                                   out + c0, keep)
         if (w) { if (vec) PMC_LAUNCH_RED(true, true); else PMC_LAUNCH_RED(true, false); }
         else   { if (vec) PMC_LAUNCH_RED(false, true); else PMC_LAUNCH_RED(false, false); }
 #undef PMC_LAUNCH_RED
@@ -139,7 +144,8 @@ enum { OP_AXPY = 0, OP_SCAL = 1, OP_COPY = 2, OP_DIAG = 3 };
 template <int OP, bool VEC>
 __global__ void __launch_bounds__(TPB)
 elementwise_kernel(double *__restrict__ Y, int64_t csY, const double *X, int64_t csX,
-                   const double *__restrict__ w, int64_t n, AlphaPack alpha, int alpha_stride) {
+                   const double *__restrict__ w, int64_t n, AlphaPack alpha, int alpha_stride, int keep) {
+    const uint64_t pol_hot = l2_policy(keep ? 2 : 0), pol_cold = l2_policy(keep ? 1 : 0);
     const int c = blockIdx.y;
     double *y = Y + (int64_t)c * csY;
     const double *x = (OP == OP_SCAL) ? nullptr : X + (int64_t)c * csX;
@@ -151,9 +157,9 @@ elementwise_kernel(double *__restrict__ Y, int64_t csY, const double *X, int64_t
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int64_t i = base + 2 * (threadIdx.x + u * TPB);
-                if (OP != OP_SCAL) xv[u] = ld_stream2(x + i);
-                if (OP == OP_AXPY || OP == OP_SCAL) yv[u] = *reinterpret_cast<const double2 *>(y + i);
-                if (OP == OP_DIAG) wv[u] = ld_stream2(w + i);
+                if (OP != OP_SCAL) xv[u] = ld_hint2_nc(x + i, pol_cold);
+                if (OP == OP_AXPY || OP == OP_SCAL) yv[u] = ld_hint2(y + i, pol_hot);
+                if (OP == OP_DIAG) wv[u] = ld_hint2_nc(w + i, pol_cold);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -163,7 +169,7 @@ elementwise_kernel(double *__restrict__ Y, int64_t csY, const double *X, int64_t
                 if (OP == OP_SCAL) { r.x = al * yv[u].x; r.y = al * yv[u].y; }
                 if (OP == OP_COPY) { r = xv[u]; }
                 if (OP == OP_DIAG) { r.x = wv[u].x * xv[u].x; r.y = wv[u].y * xv[u].y; }
-                *reinterpret_cast<double2 *>(y + i) = r;
+                st_hint2(y + i, r, pol_hot);
             }
         } else {
             const int64_t end = (base + CHUNK < n) ? base + CHUNK : n;
@@ -203,10 +209,11 @@ int launch_elementwise(pmc_ctx *ctx, double *Y, int64_t csY, const double *X, in
         bool vec = vec_ok(y, csY) && vec_ok(x, csX) && vec_ok(w, 0);
         int bx = blocks_per_col(ctx, n, kc, 8);
         dim3 grid(bx, kc);
+        const int keep = (ctx->l2_keep && (OP == OP_AXPY || OP == OP_SCAL) && k == 1 && n * 8 <= L2_KEEP_BYTES) ? 1 : 0;
         if (vec)
-            elementwise_kernel<OP, true><<<grid, TPB, 0, ctx->stream>>>(y, csY, x, csX, w, n, pack, stride);
+            elementwise_kernel<OP, true><<<grid, TPB, 0, ctx->stream>>>(y, csY, x, csX, w, n, pack, stride, keep);
         else
-            elementwise_kernel<OP, false><<<grid, TPB, 0, ctx->stream>>>(y, csY, x, csX, w, n, pack, stride);
+            elementwise_kernel<OP, false><<<grid, TPB, 0, ctx->stream>>>(y, csY, x, csX, w, n, pack, stride, keep);
         ++launches;
     }
     return pmc_after_launch(ctx, launches, flags);

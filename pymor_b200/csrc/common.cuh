@@ -25,6 +25,7 @@ struct pmc_ctx {
     double *partials;        // device, block partials of single-launch reductions
     int partials_cap;        // in doubles; followed by as many int64 (amax indices)
     void *encode_tiled;      // cuTensorMapEncodeTiled entry point
+    int l2_keep;             // keep single hot vectors L2-resident (env PMC_NO_L2_KEEP=1 disables)
 };
 
 void pmc_set_error(const char *fmt, ...);
@@ -159,6 +160,36 @@ __device__ __forceinline__ double ld_stream1(const double *p) {
     double v;
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
+}
+
+// L2 eviction-priority policies (126 MB L2): a vector that is re-used by the next kernels (the
+// column being orthogonalised in Gram-Schmidt) is loaded/stored evict_last, the operands streaming
+// past it evict_first, so that it stays L2-resident across launches.
+__device__ __forceinline__ uint64_t l2_policy(int kind /*0 normal, 1 evict_first, 2 evict_last*/) {
+    uint64_t pol;
+    if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ld_hint2_nc(const double *p, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double2 ld_hint2(const double *p, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p), "l"(pol)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_hint2(double *p, double2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol)
+                 : "memory");
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -1,5 +1,6 @@
 // Context, error reporting and TMA descriptor encoding for libpymor_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -58,6 +59,8 @@ extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
         return PMC_ERR_CUDA;
     }
     c->encode_tiled = fn;
+    const char *nk = getenv("PMC_NO_L2_KEEP");
+    c->l2_keep = (nk && nk[0] == '1') ? 0 : 1;
     *out = c;
     return PMC_OK;
 }

@@ -29,6 +29,7 @@ struct GramParams {
     int64_t rows_per_split;   // multiple of BK
     int tiles_m, tiles_n, ntiles;
     int symmetric;
+    int kA, kB;
     double *partials;         // [item][BN][BM]
 };
 
@@ -58,7 +59,6 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;
     const int g = lane >> 2, t = lane & 3;
 
     const int item = blockIdx.x;
@@ -69,6 +69,31 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int64_t r0 = (int64_t)split * p.rows_per_split;
     const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
     const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
+
+    // Warp -> 32x32 block of the tile.  The four SMSPs (warp % 4) share one FP64 tensor pipe each, so
+    // partially filled tiles are mapped such that the light blocks spread over all SMSPs:
+    //  * diagonal SYRK tiles need only the 10 blocks on/below the diagonal: warps 0..9 take them
+    //    (3/3/2/2 per SMSP), warps 10..15 only keep the barrier protocol going;
+    //  * a tile that is ragged in M (last tile row when k is not a multiple of 128) uses the
+    //    transposed map so that every SMSP gets one of the short blocks.
+    const int vm = min(BM, p.kA - ti * BM), vn = min(BN, p.kB - tj * BN);   // valid rows / cols of this tile
+    int wm, wn;
+    bool active = true;
+    if (diag) {
+        // (wm, wn) with wn <= wm, enumerated row by row: (0,0) (1,0) (1,1) (2,0) ... (3,3)
+        active = warp < 10;
+        const int w = active ? warp : 0;
+        wm = (w >= 6) ? 3 : (w >= 3) ? 2 : (w >= 1) ? 1 : 0;
+        wn = w - wm * (wm + 1) / 2;
+    } else if (vm < BM) {
+        wm = warp >> 2; wn = warp & 3;
+    } else {
+        wm = warp & 3; wn = warp >> 2;
+    }
+    int mi_cnt = (vm - wm * 32 + 7) >> 3, ni_cnt = (vn - wn * 32 + 7) >> 3;   // 8-row sub-blocks with data
+    mi_cnt = mi_cnt < 0 ? 0 : (mi_cnt > 4 ? 4 : mi_cnt);
+    ni_cnt = ni_cnt < 0 ? 0 : (ni_cnt > 4 ? 4 : ni_cnt);
+    if (mi_cnt == 0 || ni_cnt == 0) active = false;
 
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
@@ -103,13 +128,16 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    // per-thread swizzled offsets (in doubles) inside a 128-byte row, one per k-step of 4
-    const int q = g ^ ((lane >> 1) & 1);
+    // Fragment row g of an 8-row sub-block is tile row rho(g) = 2*(g&3) + (g>>2).  With the 128B TMA
+    // swizzle (16-byte chunk index ^= row & 7) the 16 lanes of each half-warp then hit 16 distinct
+    // 8-byte bank pairs: every fragment LDS.64 is conflict-free (2 wavefronts per warp, the minimum).
+    const int rho = 2 * (g & 3) + (g >> 2);
+    const int h = (lane >> 1) & 1, e = lane & 1;
     int swz[4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) swz[ks] = ((((ks * 2) ^ q) << 1) + (lane & 1));
-    const int rowA = (wm * 32 + g) * BK;
-    const int rowB = (wn * 32 + g) * BK;
+    for (int ks = 0; ks < 4; ++ks) swz[ks] = ((((ks * 2 + h) ^ rho) << 1) + e);
+    const int rowA = (wm * 32 + rho) * BK;
+    const int rowB = (wn * 32 + rho) * BK;
 
     for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % STAGES;
@@ -120,41 +148,57 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             issue(kt - 1 + STAGES);
         }
         mbar_wait(&full[s], (kt / STAGES) & 1);
-        const double *a_s = sA + s * TILE_ELEMS + rowA;
-        const double *b_s = (diag ? sA : sB) + s * TILE_ELEMS + rowB;
-        const double *w_s = sW + s * BK + t;
+        if (active) {
+            const double *a_s = sA + s * TILE_ELEMS + rowA;
+            const double *b_s = (diag ? sA : sB) + s * TILE_ELEMS + rowB;
+            const double *w_s = sW + s * BK + t;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            double a[4], b[4];
+            for (int ks = 0; ks < 4; ++ks) {
+                double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * BK + swz[ks]];
+                for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[mi * 8 * BK + swz[ks]];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = b_s[ni * 8 * BK + swz[ks]];
-            if (WEIGHTED) {
-                const double wv = w_s[ks * 4];
+                for (int ni = 0; ni < 4; ++ni) b[ni] = b_s[ni * 8 * BK + swz[ks]];
+                if (WEIGHTED) {
+                    const double wv = w_s[ks * 4];
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) b[ni] *= wv;
+                    for (int ni = 0; ni < 4; ++ni) b[ni] *= wv;
+                }
+                if (mi_cnt == 4 && ni_cnt == 4) {
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                } else {
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+                        if (mi < mi_cnt) {
+#pragma unroll
+                            for (int ni = 0; ni < 4; ++ni)
+                                if (ni < ni_cnt) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                        }
+                }
             }
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
-    // epilogue: partial tile, column-major [j][i]
-    double *out = p.partials + (size_t)item * (BM * BN);
+    // epilogue: partial tile, column-major [j][i]; blocks nobody reads later are not written
+    if (active) {
+        double *out = p.partials + (size_t)item * (BM * BN);
+        const int jc0 = 2 * ((2 * t) & 3) + ((2 * t) >> 2);            // rho(2t)
+        const int jc1 = 2 * ((2 * t + 1) & 3) + ((2 * t + 1) >> 2);    // rho(2t+1)
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int i = wm * 32 + mi * 8 + g;
-            const int j = wn * 32 + ni * 8 + 2 * t;
-            out[(size_t)j * BM + i] = acc[mi][ni][0];
-            out[(size_t)(j + 1) * BM + i] = acc[mi][ni][1];
-        }
+            for (int ni = 0; ni < 4; ++ni) {
+                const int i = wm * 32 + mi * 8 + rho;
+                const int j = wn * 32 + ni * 8;
+                out[(size_t)(j + jc0) * BM + i] = acc[mi][ni][0];
+                out[(size_t)(j + jc1) * BM + i] = acc[mi][ni][1];
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -267,6 +311,8 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
 
     GramParams p;
     p.n = n;
+    p.kA = kA;
+    p.kB = kB;
     p.symmetric = sym ? 1 : 0;
     p.tiles_m = (kA + T - 1) / T;
     p.tiles_n = (kB + T - 1) / T;

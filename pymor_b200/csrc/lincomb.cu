@@ -98,12 +98,15 @@ lincomb_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int dd = fperm + 4 * h;
             a_off[ks][h] = i * 16 + ((((dd >> 1) ^ (i & 7)) << 1) | (dd & 1));
         }
-    // C fragment: same K-major swizzled pattern as the Gram kernel
-    const int q = g ^ ((lane >> 1) & 1);
+    // C fragment: same K-major swizzled pattern as the Gram kernel; fragment column g is tile column
+    // rho(g) = 2*(g&3) + (g>>2), which makes each half-warp's 16 loads hit 16 distinct bank pairs
+    const int rho = 2 * (g & 3) + (g >> 2);
     int c_off[4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) c_off[ks] = ((((ks * 2) ^ q) << 1) + (lane & 1));
-    const int rowC = (wj * 32 + g) * LK;
+    for (int ks = 0; ks < 4; ++ks) c_off[ks] = ((((ks * 2 + ((lane >> 1) & 1)) ^ rho) << 1) + (lane & 1));
+    const int rowC = (wj * 32 + rho) * LK;
+    int ni_cnt = (min(LN, p.m - j0) - wj * 32 + 7) >> 3;      // 8-column sub-blocks with data
+    ni_cnt = ni_cnt < 0 ? 0 : (ni_cnt > 4 ? 4 : ni_cnt);
 
     for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % LSTAGES;
@@ -115,17 +118,36 @@ lincomb_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&full[s], (kt / LSTAGES) & 1);
         const double *a_s = sA + s * A_TILE_ELEMS + (2 * wd) * A_BOX_ELEMS;
         const double *c_s = sC + s * C_TILE_ELEMS + rowC;
+        if (ni_cnt == 4) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            double a[4], b[4];
+            for (int ks = 0; ks < 4; ++ks) {
+                double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[(mi >> 1) * A_BOX_ELEMS + a_off[ks][mi & 1]];
+                for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[(mi >> 1) * A_BOX_ELEMS + a_off[ks][mi & 1]];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = c_s[ni * 8 * LK + c_off[ks]];
+                for (int ni = 0; ni < 4; ++ni) b[ni] = c_s[ni * 8 * LK + c_off[ks]];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+        } else if (ni_cnt > 0) {
+            // last column tile when m is not a multiple of 128: skip the 8-column sub-blocks without data
+            // (the four short warps sit on four different SMSPs, so the whole CTA gets faster)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[(mi >> 1) * A_BOX_ELEMS + a_off[ks][mi & 1]];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = c_s[ni * 8 * LK + c_off[ks]];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    if (ni < ni_cnt) {
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    }
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -138,9 +160,11 @@ lincomb_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (d >= p.n) continue;
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
-            const int j = j0 + wj * 32 + ni * 8 + 2 * t;
-            if (j < p.m) p.R[(int64_t)j * p.csR + d] = acc[mi][ni][0];
-            if (j + 1 < p.m) p.R[(int64_t)(j + 1) * p.csR + d] = acc[mi][ni][1];
+            const int jb = j0 + wj * 32 + ni * 8;
+            const int ja = jb + 2 * ((2 * t) & 3) + ((2 * t) >> 2);          // rho(2t)
+            const int jc = jb + 2 * ((2 * t + 1) & 3) + ((2 * t + 1) >> 2);  // rho(2t+1)
+            if (ja < p.m) p.R[(int64_t)ja * p.csR + d] = acc[mi][ni][0];
+            if (jc < p.m) p.R[(int64_t)jc * p.csR + d] = acc[mi][ni][1];
         }
     }
 }
