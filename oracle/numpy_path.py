@@ -272,6 +272,65 @@ def project(M, range_basis, source_basis, W=None):
     return apply2(M, rb, source_basis)                     # :143
 
 
+def shifted_chol_qr(A, W=None, return_R=False, maxiter=3, offset=0, product_norm=None, recompute_shift=False):
+    """Shifted CholeskyQR3 (src/pymor/algorithms/chol_qr.py:16-168; kernels :205-252; "next" row N1 of
+    SURVEY.md §8f).  ``product_norm`` must be given when ``W`` is.  Note: in the reference the default
+    (non-recomputing) kernel cannot actually apply a shift -- it raises AttributeError at :227 -- so the
+    shifted branch is only pinned for ``recompute_shift=True``."""
+    A = np.array(A, order='F', copy=True)
+    dim, k = A.shape
+    if offset == k:
+        return (A, np.eye(k)) if return_R else A
+
+    def gram_blocks():                                     # chol_qr.py:159-168
+        G = inner(A, A[:, offset:], W)
+        return G[:offset], G[offset:]
+
+    def shift_for(X):                                      # chol_qr.py:178-203
+        n = len(X)
+        eps = np.finfo(np.float64).eps
+        shift = 11 * eps
+        shift *= (dim * n + n * (n + 1)) if W is None else \
+            (2 * dim * np.sqrt(dim * n) + n * (n + 1)) * product_norm
+        top = spla.eigh(X, eigvals_only=True, subset_by_index=[n - 1, n - 1])[0]
+        return max(shift * top, eps)
+
+    B, X = gram_blocks()
+    shift = None
+    Bi = Ri = None
+    for it in range(1, maxiter + 1):                       # chol_qr.py:113-146
+        X = X - B.T @ B
+        cur = 0.0
+        for attempt in range(10):                          # kernels :208-224 / :232-252
+            try:
+                Rx = spla.cholesky(X + np.eye(len(X)) * cur if recompute_shift else X)
+                break
+            except spla.LinAlgError:
+                if recompute_shift:
+                    cur = shift_for(X) if attempt == 0 else cur * 10
+                else:
+                    if not shift:
+                        shift = shift_for(X)
+                    X[np.diag_indices_from(X)] += shift
+        else:
+            raise AccuracyError('Failed to compute a Cholesky factorization of X.')
+        Rinv = spla.solve_triangular(Rx, np.eye(len(Rx)))
+        A[:, offset:] = A[:, :offset] @ (-B @ Rinv) + A[:, offset:] @ Rinv
+        if it == 1:
+            Bi, Ri = B, Rx
+        else:
+            Bi = Bi + B @ Ri
+            Ri = Rx @ Ri
+        if it < maxiter:
+            B, X = gram_blocks()
+    if not return_R:
+        return A
+    R = np.eye(k)
+    R[:offset, offset:] = Bi
+    R[offset:, offset:] = Ri
+    return A, R
+
+
 # ------------------------------------------------------------------------------------------------
 # parity metrics named by the north star (SURVEY.md §8c)
 # ------------------------------------------------------------------------------------------------

@@ -11,6 +11,9 @@ touch raw data, like their reference counterparts):
 * :func:`qr_svd`                -- src/pymor/algorithms/svd_va.py:103-168
 * :func:`pod`                   -- src/pymor/algorithms/pod.py:16-90
 * :func:`project`               -- src/pymor/algorithms/projection.py:28-85 (rule ``action_apply_basis``)
+* :func:`shifted_chol_qr`       -- src/pymor/algorithms/chol_qr.py:16-252 ("next" row N1: the GEMM-bound
+  orthonormalisation -- three Gramians + three block lincombs instead of k^2 dot/axpy pairs with a
+  host sync each, i.e. the variant that scales over DOF-sharded GPUs)
 """
 from __future__ import annotations
 
@@ -157,3 +160,109 @@ def project(op, range_basis, source_basis, product=None):
     if rb is None:
         return op.apply(source_basis)
     return op.apply2(rb, source_basis)
+
+
+def _product_norm_estimate(product, iters=20):
+    """Spectral norm of an SPD product operator by power iteration (the reference calls
+    ``pymor.algorithms.eigs.eigs(product, k=1)``, chol_qr.py:185-187; any estimate of the same
+    quantity serves: it only scales the diagonal shift)."""
+    v = product.source.random(1, distribution='normal')
+    lam = 1.0
+    for _ in range(iters):
+        v.scal(1.0 / v.norm()[0])
+        v = product.apply(v)
+        lam = v.norm()[0]
+    return float(lam)
+
+
+class _ShiftedCholesky:
+    """Cholesky factor of a Gramian, shifted on breakdown (chol_qr.py:171-252)."""
+    INNER_ITERS = 10
+
+    def __init__(self, dim, product, product_norm, check_finite, recompute):
+        self.dim, self.product, self.product_norm = dim, product, product_norm
+        self.check_finite, self.recompute, self.shift = check_finite, recompute, None
+
+    def _compute_shift(self, X):
+        m, n = self.dim, len(X)
+        eps = np.finfo(X.dtype).eps
+        shift = 11 * eps
+        if self.product is None:
+            shift *= m * n + n * (n + 1)
+        else:
+            if self.product_norm is None:
+                self.product_norm = np.sqrt(_product_norm_estimate(self.product))
+            shift *= (2 * m * np.sqrt(m * n) + n * (n + 1)) * self.product_norm
+        top = spla.eigh(X, eigvals_only=True, subset_by_index=[n - 1, n - 1], driver='evr')[0]
+        return max(shift * top, eps)
+
+    def apply(self, X):
+        shift = 0.0
+        for it in range(self.INNER_ITERS):
+            try:
+                M = X + np.eye(len(X)) * shift if self.recompute else X
+                return spla.cholesky(M, overwrite_a=False, check_finite=self.check_finite)
+            except spla.LinAlgError:
+                logger.warning('Cholesky factorization broke down! Matrix is ill-conditioned.')
+                if self.recompute:
+                    shift = self._compute_shift(X) if it == 0 else shift * 10
+                else:
+                    if not self.shift:
+                        self.shift = self._compute_shift(X)
+                    X[np.diag_indices_from(X)] += self.shift
+        raise AccuracyError('Failed to compute a Cholesky factorization of X.')
+
+
+def shifted_chol_qr(A, product=None, return_R=False, maxiter=3, offset=0, orth_tol=None,
+                    recompute_shift=False, check_finite=True, copy=True, product_norm=None):
+    """Shifted CholeskyQR(3): Gramian -> Cholesky (diagonally shifted on breakdown) -> block
+    lincomb with the inverse factor, repeated ``maxiter`` times.  Same arguments and behaviour as the
+    reference; all n-sized work is GEMM-class (``inner``/``gramian``/``lincomb``/``append``)."""
+    assert 0 <= offset <= len(A)
+    assert A.dim >= len(A)
+    assert 0 < maxiter
+    assert orth_tol is None or 0 < orth_tol
+    if copy:
+        A = A.copy()
+    k = len(A)
+    if offset == k:
+        return (A, np.eye(k)) if return_R else A
+    chol = _ShiftedCholesky(A.dim, product, product_norm, check_finite, recompute_shift)
+
+    def gram_blocks():
+        G = A.inner(A[offset:], product=product)
+        return G[:offset].astype(np.float64, copy=False), G[offset:].astype(np.float64, copy=False)
+
+    B, X = gram_blocks()
+    Bi = Ri = None
+    it = 1
+    while it <= maxiter:
+        X = X - B.conj().T @ B
+        Rx = chol.apply(X)
+        Rinv = spla.solve_triangular(Rx, np.eye(len(Rx)), lower=False, check_finite=check_finite)
+        todo = A[:offset].lincomb(-B @ Rinv) + A[offset:].lincomb(Rinv)
+        del A[offset:]
+        A.append(todo)
+        if it == 1:
+            Bi, Ri = B, Rx
+        else:
+            Bi = Bi + B @ Ri
+            Ri = Rx @ Ri
+        if it < maxiter:
+            B, X = gram_blocks()
+        elif orth_tol is not None:
+            X = A[offset:].gramian(product=product)
+        if orth_tol is not None:
+            res = spla.norm(X - np.eye(k - offset), ord='fro', check_finite=check_finite)
+            if res <= orth_tol * np.sqrt(k):
+                break
+            if it == maxiter:
+                raise AccuracyError('Orthonormality could not be achieved within the given tolerance. '
+                                    'Consider increasing maxiter or enabling recompute_shift.')
+        it += 1
+    if not return_R:
+        return A
+    R = np.eye(k)
+    R[:offset, offset:] = Bi
+    R[offset:, offset:] = Ri
+    return A, R

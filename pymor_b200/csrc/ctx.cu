@@ -61,6 +61,8 @@ extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
     c->encode_tiled = fn;
     const char *nk = getenv("PMC_NO_L2_KEEP");
     c->l2_keep = (nk && nk[0] == '1') ? 0 : 1;
+    const char *go = getenv("PMC_GRAM_OPTS");
+    c->gram_opts = go ? atoi(go) : 0;
     *out = c;
     return PMC_OK;
 }

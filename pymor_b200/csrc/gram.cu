@@ -30,6 +30,7 @@ struct GramParams {
     int tiles_m, tiles_n, ntiles;
     int symmetric;
     int kA, kB;
+    int opts;                 // ablation switches (env PMC_GRAM_OPTS): 1 no diag skip, 2 no empty-block skip, 4 no transpose
     double *partials;         // [item][BN][BM]
 };
 
@@ -70,30 +71,29 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
     const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
 
-    // Warp -> 32x32 block of the tile.  The four SMSPs (warp % 4) share one FP64 tensor pipe each, so
-    // partially filled tiles are mapped such that the light blocks spread over all SMSPs:
+    // Warp -> 32x32 block of the tile.  Each SMSP (warp % 4) has its own FP64 tensor pipe, so when
+    // only some blocks carry work they are spread over the SMSPs:
     //  * diagonal SYRK tiles need only the 10 blocks on/below the diagonal: warps 0..9 take them
-    //    (3/3/2/2 per SMSP), warps 10..15 only keep the barrier protocol going;
-    //  * a tile that is ragged in M (last tile row when k is not a multiple of 128) uses the
-    //    transposed map so that every SMSP gets one of the short blocks.
+    //    (3/3/2/2 per SMSP), warps 10..15 only keep the barrier protocol going (measured: -5 %);
+    //  * blocks entirely beyond kA / kB are skipped; a tile that is short in M uses the transposed map
+    //    so that the surviving blocks sit on all four SMSPs.
+    // (Skipping at 8-row granularity inside a block was measured to be SLOWER -- the predicated DMMA
+    // sequence issues worse than the straight-line one -- so partially filled blocks run in full.)
     const int vm = min(BM, p.kA - ti * BM), vn = min(BN, p.kB - tj * BN);   // valid rows / cols of this tile
     int wm, wn;
     bool active = true;
-    if (diag) {
+    if (diag && !(p.opts & 1)) {
         // (wm, wn) with wn <= wm, enumerated row by row: (0,0) (1,0) (1,1) (2,0) ... (3,3)
         active = warp < 10;
         const int w = active ? warp : 0;
         wm = (w >= 6) ? 3 : (w >= 3) ? 2 : (w >= 1) ? 1 : 0;
         wn = w - wm * (wm + 1) / 2;
-    } else if (vm < BM) {
+    } else if (vm <= BM - 32 && !(p.opts & 4)) {
         wm = warp >> 2; wn = warp & 3;
     } else {
         wm = warp & 3; wn = warp >> 2;
     }
-    int mi_cnt = (vm - wm * 32 + 7) >> 3, ni_cnt = (vn - wn * 32 + 7) >> 3;   // 8-row sub-blocks with data
-    mi_cnt = mi_cnt < 0 ? 0 : (mi_cnt > 4 ? 4 : mi_cnt);
-    ni_cnt = ni_cnt < 0 ? 0 : (ni_cnt > 4 ? 4 : ni_cnt);
-    if (mi_cnt == 0 || ni_cnt == 0) active = false;
+    if (!(p.opts & 2) && (wm * 32 >= vm || wn * 32 >= vn)) active = false;
 
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
@@ -164,20 +164,10 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) b[ni] *= wv;
                 }
-                if (mi_cnt == 4 && ni_cnt == 4) {
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-                } else {
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
-                        if (mi < mi_cnt) {
-#pragma unroll
-                            for (int ni = 0; ni < 4; ++ni)
-                                if (ni < ni_cnt) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-                        }
-                }
+                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
         }
         __syncwarp();
@@ -313,6 +303,7 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
     p.n = n;
     p.kA = kA;
     p.kB = kB;
+    p.opts = ctx->gram_opts;
     p.symmetric = sym ? 1 : 0;
     p.tiles_m = (kA + T - 1) / T;
     p.tiles_n = (kB + T - 1) / T;

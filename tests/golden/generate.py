@@ -192,11 +192,45 @@ def thermalblock():
     np.savez_compressed(OUT / 'thermalblock.npz', **out)
 
 
+def chol_qr():
+    """"Next" row N1: shifted CholeskyQR3 (src/pymor/algorithms/chol_qr.py:16)."""
+    from pymor.algorithms.chol_qr import shifted_chol_qr
+    rng = np.random.default_rng(6)
+    dim, k = 257, 12
+    Gn = rng.standard_normal((dim, k)) / np.sqrt(dim)
+    Qk, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    out = {}
+    # The ill-conditioned input needs the diagonal shift.  With the default kernel the reference
+    # raises AttributeError there (BasicShiftedCholQRKernel reads `self.shift` before ever setting it,
+    # chol_qr.py:227), so the shifted branch is pinned through recompute_shift=True.
+    for tag, decades in (('mild', 3), ('ill', 9)):
+        A = np.asfortranarray(Gn @ np.diag(10.0 ** (-decades * np.arange(k) / (k - 1))) @ Qk.T)
+        w = rng.uniform(0.5, 1.5, dim)
+        sp = NumpyVectorSpace(dim)
+        out[f'A_{tag}'], out[f'w_{tag}'] = A, w
+        rs = tag == 'ill'
+        Q, R = shifted_chol_qr(sp.from_numpy(A.copy()), return_R=True, recompute_shift=rs)
+        out[f'Q_euclid_{tag}'], out[f'R_euclid_{tag}'] = Q.to_numpy(), R
+        Q, R = shifted_chol_qr(sp.from_numpy(A.copy()), product=NumpyMatrixOperator(sps.diags(w).tocsr()),
+                               return_R=True, product_norm=float(np.sqrt(w.max())), recompute_shift=rs)
+        out[f'Q_diag_{tag}'], out[f'R_diag_{tag}'] = Q.to_numpy(), R
+    Q0 = shifted_chol_qr(sp.from_numpy(out['A_mild'][:, :5].copy()))
+    Q0.append(sp.from_numpy(out['A_mild'][:, 5:].copy()))
+    Q1, R1 = shifted_chol_qr(Q0, offset=5, return_R=True)
+    out['Q_offset'], out['R_offset'] = Q1.to_numpy(), R1
+    np.savez_compressed(OUT / 'chol_qr.npz', **out)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     vecops()
     gs()
     pods()
     projection()
     thermalblock()
+    chol_qr()
     for f in sorted(OUT.glob('*.npz')):
         print(f.name, f.stat().st_size)

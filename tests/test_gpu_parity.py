@@ -204,16 +204,26 @@ def test_gram_schmidt_golden(loaded_lib, name):
     Q, R = alg.gram_schmidt(sp.from_numpy(g['A']), product=prod, return_R=True)
     Qh, Qref = Q.to_numpy(), g[f'Q_{name}']
     assert Qh.shape == Qref.shape                          # the same vectors were removed
-    np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
-    # Column 4 of the input is column 1 plus 1e-9 noise: its orthogonalised direction is the
+    # Column 4 of the input is column 1 plus 1e-9 noise: its orthogonalised direction q_4 is the
     # normalised O(1e-9) remainder, i.e. conditioned like 1e9 * eps w.r.t. ANY change of summation
-    # order (the reference itself moves by that much between BLAS builds).  All other columns: 1e-11.
-    others = [c for c in range(Qh.shape[1]) if c != 4]
-    np.testing.assert_allclose(Qh[:, others], Qref[:, others], atol=1e-11)
-    np.testing.assert_allclose(Qh[:, 4], Qref[:, 4], atol=1e-6)
+    # order (the reference itself moves by that much between BLAS builds); the coefficients R[4, :]
+    # along it and, through them, the later vectors inherit a perturbation of that size.  So this
+    # (deliberately nasty) input is compared at cond * eps; the well-conditioned sub-problem below and
+    # the invariants are pinned tightly.
+    np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-5)
+    np.testing.assert_allclose(Qh, Qref, atol=1e-6)
+    first = [0, 1, 2, 3]                                   # before the near-dependency: exact parity
+    np.testing.assert_allclose(Qh[:, first], Qref[:, first], atol=1e-12)
+    np.testing.assert_allclose(R[:4, :4], g[f'R_{name}'][:4, :4], atol=1e-11)
     np.testing.assert_allclose(Qh @ R, g['A'], atol=1e-12)     # A = Q R holds to rounding (removed columns too)
     # orthogonality error no worse than the reference's (up to a factor for rounding noise)
     assert O.orthogonality_error(Q.to_numpy(), W) <= max(4 * O.orthogonality_error(g[f'Q_{name}'], W), 1e-14)
+    if name == 'euclid':
+        # well-conditioned sub-problem incl. the `offset` path used by reductors' extend_basis
+        Q0 = alg.gram_schmidt(sp.from_numpy(g['A'][:, :4]))
+        Q0.append(sp.from_numpy(g['A'][:, 10:]))
+        Q1 = alg.gram_schmidt(Q0, offset=4, copy=False)
+        np.testing.assert_allclose(Q1.to_numpy(), g['Q_offset'], atol=1e-11)
 
 
 @pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
@@ -320,3 +330,36 @@ def test_full_size_properties(loaded_lib):
     R = U.lincomb(coeff)
     R.axpy(-1.0, A[:8])
     assert np.max(R.norm(prod) / A[:8].norm(prod)) < 1e-9
+
+
+def test_shifted_chol_qr_golden(loaded_lib):
+    """"Next" row N1 on the device: CholeskyQR3 = 3 Gramians + 3 block lincombs, no per-pair host sync."""
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaDiagonalOperator
+    g = load_golden('chol_qr')
+    for tag, tolQ in (('mild', 1e-11), ('ill', 1e-5)):
+        A, w = g[f'A_{tag}'], g[f'w_{tag}']
+        sp = space_of(A.shape[0])
+        rs = tag == 'ill'
+        Q, R = alg.shifted_chol_qr(sp.from_numpy(A), return_R=True, recompute_shift=rs)
+        np.testing.assert_allclose(R, g[f'R_euclid_{tag}'], atol=1e-12)
+        np.testing.assert_allclose(Q.to_numpy(), g[f'Q_euclid_{tag}'], atol=tolQ)
+        prod = CudaDiagonalOperator(w, sp)
+        Q, R = alg.shifted_chol_qr(sp.from_numpy(A), product=prod, return_R=True,
+                                   product_norm=float(np.sqrt(w.max())), recompute_shift=rs)
+        np.testing.assert_allclose(R, g[f'R_diag_{tag}'], atol=1e-12)
+        assert O.orthogonality_error(Q.to_numpy(), w) < 1e-13
+        np.testing.assert_allclose(Q.to_numpy() @ R, A, atol=1e-13)
+    # at scale: 1M x 128, orthonormal to rounding, A = QR
+    import torch
+    n, k = 1_000_000, 128
+    sp = space_of(n)
+    A = sp.random_device(k, seed=5, scale=1.0 / np.sqrt(n))
+    A.axpy(2.0, sp.random_device(1, seed=6, scale=1.0 / np.sqrt(n)))
+    w = torch.rand(n, device='cuda', dtype=torch.float64) + 0.5
+    prod = CudaDiagonalOperator(w, sp)
+    Q, R = alg.shifted_chol_qr(A, product=prod, return_R=True, product_norm=float(np.sqrt(1.5)))
+    assert np.max(np.abs(Q.gramian(prod) - np.eye(k))) < 1e-13
+    D = Q.lincomb(R)
+    D.axpy(-1.0, A)
+    assert np.max(D.norm(prod) / A.norm(prod)) < 1e-13

@@ -312,3 +312,31 @@ def test_pymor_algorithms_run_unchanged():
     r = _run('run_contract.py', str(ROOT / 'tests' / 'reference_contract' / 'pymor_mode_checks.py'))
     tail = r.stdout[-3000:]
     assert r.returncode == 0, tail
+
+
+def test_standalone_shifted_chol_qr_golden(emu):
+    """"Next" row N1 through the stand-alone driver (Gramian / lincomb / append / delete only)."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    g = load_golden('chol_qr')
+    for tag, tolQ in (('mild', 1e-12), ('ill', 1e-6)):
+        A, w = g[f'A_{tag}'], g[f'w_{tag}']
+        sp = space_of(A.shape[0])
+        rs = tag == 'ill'
+        Q, R = alg.shifted_chol_qr(sp.from_numpy(A), return_R=True, recompute_shift=rs)
+        np.testing.assert_allclose(R, g[f'R_euclid_{tag}'], atol=1e-12)
+        np.testing.assert_allclose(Q.to_numpy(), g[f'Q_euclid_{tag}'], atol=tolQ)
+        prod = CudaDiagonalOperator(w, sp)
+        Q, R = alg.shifted_chol_qr(sp.from_numpy(A), product=prod, return_R=True,
+                                   product_norm=float(np.sqrt(w.max())), recompute_shift=rs)
+        np.testing.assert_allclose(R, g[f'R_diag_{tag}'], atol=1e-12)
+        np.testing.assert_allclose(Q.to_numpy(), g[f'Q_diag_{tag}'], atol=tolQ)
+        assert O.orthogonality_error(Q.to_numpy(), w) < 1e-13
+    sp = space_of(g['A_mild'].shape[0])
+    Q0 = alg.shifted_chol_qr(sp.from_numpy(g['A_mild'][:, :5]))
+    Q0.append(sp.from_numpy(g['A_mild'][:, 5:]))
+    Q1, R1 = alg.shifted_chol_qr(Q0, offset=5, return_R=True)
+    np.testing.assert_allclose(Q1.to_numpy(), g['Q_offset'], atol=1e-12)
+    np.testing.assert_allclose(R1, g['R_offset'], atol=1e-12)
+    # the default kernel applies the shift as well (the reference raises AttributeError there)
+    Q = alg.shifted_chol_qr(sp.from_numpy(g['A_ill']))
+    assert O.orthogonality_error(Q.to_numpy()) < 1e-12

@@ -160,3 +160,24 @@ def test_oracle_against_live_reference(rng):
         Uo, so = O.pod(A, w)
         np.testing.assert_allclose(so, s, rtol=1e-10)
         assert O.subspace_angle(U.to_numpy(), Uo, w) < 1e-8
+
+
+def test_shifted_chol_qr_golden():
+    """"Next" row N1.  R is pinned to 1e-13; Q of the ill-conditioned input (cond 1e9) only to
+    cond * eps, its orthogonality and A = Q R to rounding."""
+    g = load_golden('chol_qr')
+    for tag, tolQ in (('mild', 1e-12), ('ill', 1e-6)):
+        A, w = g[f'A_{tag}'], g[f'w_{tag}']
+        rs = tag == 'ill'
+        Q, R = O.shifted_chol_qr(A, return_R=True, recompute_shift=rs)
+        np.testing.assert_allclose(R, g[f'R_euclid_{tag}'], atol=1e-13)
+        np.testing.assert_allclose(Q, g[f'Q_euclid_{tag}'], atol=tolQ)
+        assert O.orthogonality_error(Q) < 1e-14
+        Q, R = O.shifted_chol_qr(A, w, return_R=True, product_norm=float(np.sqrt(w.max())), recompute_shift=rs)
+        np.testing.assert_allclose(R, g[f'R_diag_{tag}'], atol=1e-13)
+        np.testing.assert_allclose(Q, g[f'Q_diag_{tag}'], atol=tolQ)
+        np.testing.assert_allclose(Q @ R, A, atol=1e-13)
+    Q0 = O.shifted_chol_qr(g['A_mild'][:, :5])
+    Q1, R1 = O.shifted_chol_qr(np.hstack([Q0, g['A_mild'][:, 5:]]), offset=5, return_R=True)
+    np.testing.assert_allclose(Q1, g['Q_offset'], atol=1e-12)
+    np.testing.assert_allclose(R1, g['R_offset'], atol=1e-13)

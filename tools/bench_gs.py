@@ -34,12 +34,22 @@ def main():
     from pymor_b200.operators import CudaDiagonalOperator
     from pymor_b200.vectorarray import CudaVectorArrayImpl, CudaVectorSpace
     n, k = args.n, args.k
-    space = CudaVectorSpace(n)
+    world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    comm = None
+    if world > 1:                                   # torchrun: rows sharded over ranks (strong scaling)
+        import torch.distributed as dist
+
+        from pymor_b200.dist import ProcessGroupComm
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        comm = ProcessGroupComm()
+    space = CudaVectorSpace(n, device=torch.device('cuda', torch.cuda.current_device()), comm=comm)
     A = space.random_device(k, seed=1, scale=1.0 / np.sqrt(n))
     s = space.random_device(1, seed=2, scale=1.0 / np.sqrt(n))
     A.axpy(2.0, s)
-    gen = torch.Generator(device='cuda').manual_seed(3)
-    w = torch.rand(n, generator=gen, device='cuda', dtype=torch.float64) + 0.5
+    gen = torch.Generator(device=space.device).manual_seed(3 + rank)
+    w = torch.rand(space.local_dim, generator=gen, device=space.device, dtype=torch.float64) + 0.5
     prod = CudaDiagonalOperator(w, space)
 
     counts = {'pairwise_inner': 0, 'axpy': 0, 'scal': 0}
@@ -68,11 +78,11 @@ def main():
     err = float(np.max(np.abs(Q.gramian(prod) - np.eye(len(Q)))))
     peaks = ROOT / 'MEASURED_PEAKS.json'
     hbm = json.loads(peaks.read_text())['hbm_gbs'] if peaks.exists() else 6650.0
-    out = {'workload': f'gram_schmidt {n} x {k}, diag-W, re-iterated', 'seconds': dt, 'pair_steps': pair_steps,
+    out = {'workload': f'gram_schmidt {n} x {k}, diag-W, re-iterated', 'n_gpus': world, 'seconds': dt, 'pair_steps': pair_steps,
            'weighted_norms': norms, 'scals': counts['scal'], 'algorithmic_bytes': nbytes,
            'achieved_gbs': nbytes / dt * 1e-9, 'hbm_peak_gbs': hbm,
            'peak_source': 'MEASURED_PEAKS.json' if peaks.exists() else 'fallback 6650 GB/s',
-           'frac': nbytes / dt * 1e-9 / hbm, 'us_per_pair_step': dt / max(pair_steps, 1) * 1e6,
+           'frac': nbytes / dt * 1e-9 / (hbm * world), 'us_per_pair_step': dt / max(pair_steps, 1) * 1e6,
            'gpu_launches': launches, 'orth_err': err, 'len_Q': len(Q)}
     if args.cpu_n:
         from oracle import numpy_path as O
@@ -85,7 +95,10 @@ def main():
         tc = time.perf_counter() - t0
         out['cpu_baseline'] = {'rows': args.cpu_n, 'seconds': tc, 'pair_steps': st['pair_steps'], 'kind': 'port',
                                'cores': os.cpu_count(), 'extrapolated_seconds_full_n': tc * n / args.cpu_n}
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
