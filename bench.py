@@ -63,6 +63,14 @@ def cpu_pod_sample(n, k, seed=42):
     return dt, U.shape[1]
 
 
+def psutil_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 64 << 30
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -282,16 +290,26 @@ def run_cuda(args):
     try:
         if args.no_e2e:
             raise RuntimeError('skipped (--no-e2e)')
-        host = torch.empty((k, n_local), dtype=torch.float64, pin_memory=True)
-        host.copy_(A.to_torch())
+        # The snapshots start in pinned host memory and arrive in column chunks, the way pyMOR's
+        # reduce_pod builds its array (`snapshots.append(fom.solve(mu))`).  One rank's shard is 80 GB;
+        # with N ranks on one host N x 80 GB do not fit into RAM, so the pinned buffer holds as many
+        # snapshot columns as a 45 % share of the free host memory allows and is re-used for the
+        # later chunks (every byte is still copied host -> device inside the timed region).
+        avail = psutil_available()
+        k_host = int(min(k, max(1, (0.45 * avail / world) // (n_local * 8))))
+        host = torch.empty((k_host, n_local), dtype=torch.float64, pin_memory=True)
+        host.copy_(A.to_torch()[:k_host])
         del A
         torch.cuda.empty_cache()
-        host_np = host.numpy().T                          # (n_local, k) Fortran-ordered view
-        h2d = host.numel() * 8
+        host_np = host.numpy().T                          # (n_local, k_host) Fortran-ordered view
+        h2d = k * n_local * 8
         last = {}
 
         def e2e_step():
-            arr = space.from_local_numpy(host_np)          # public API: host shard -> HBM (one DMA)
+            arr = space.empty(reserve=k)
+            for c0 in range(0, k, k_host):                # public API: host chunk -> HBM, appended
+                kc = min(k_host, k - c0)
+                arr.append(space.from_local_numpy(host_np[:, :kc]), remove_from_other=True)
             U, s = pod_step(arr)
             last['s'] = np.array(s)                       # singular values arrive on the host
             mm = len(U)
@@ -306,7 +324,9 @@ def run_cuda(args):
         e2e = {'value': pod_flops(n_global, k, m2) / (t_e2e * 1e-3) * 1e-12, 'unit': 'TFLOP/s',
                'h2d_bytes_per_step': int(h2d + k * k * 8), 'd2h_bytes_per_step': int(2 * k * k * 8 + 8 * k),
                'ms_per_step': t_e2e, 'steps': n_e2e,
-               'note': 'snapshots start in pinned host memory; H2D of the shard, Gram/check D2H and the '
+               'host_chunk_columns': k_host,
+               'note': 'snapshots start in pinned host memory and are appended in chunks of host_chunk_columns '
+                       'columns (from_local_numpy + append); H2D of the shard, Gram/check D2H and the '
                        'coefficient H2D are inside the timed region; the modes stay on the device'}
         del host_np
     except Exception as exc:                              # e.g. not enough host RAM to pin the shard
@@ -349,7 +369,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
-    ap.add_argument('--n', type=int, default=10_000_000, help='DOFs per GPU')
+    ap.add_argument('--dofs', dest='n', type=int, default=10_000_000, help='DOFs per GPU')
     ap.add_argument('--k', type=int, default=1000, help='snapshots')
     ap.add_argument('--cpu-sample', type=int, default=150_000, help='rows of the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')

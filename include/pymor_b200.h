@@ -129,19 +129,30 @@ int pmc_amax(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n, i
 int pmc_diag_apply(pmc_ctx *ctx, const double *w, const double *X, int64_t csX, double *Y,
                    int64_t csY, int32_t k, int64_t n, uint32_t flags);
 
-/* CSR operator.apply:  Y[r + c*csY] = sum_{p in row r} vals[p] * X[colidx[p] + c*csX].
- * rowptr (int64, nrows+1), colidx (int32), vals (fp64) are DEVICE arrays.  Replaces
- * NumpyMatrixOperator.apply for scipy sparse matrices (operators/numpy.py:232-237). */
+/* CSR operator.apply:  Y[r + c*csY] = sum_{p in row r} vals[p] * x(colidx[p], c).
+ * rowptr (int64, nrows+1), colidx (int32), vals (fp64) are DEVICE arrays of this rank's row block.
+ * Column indices < nrows address the rank's own rows, x = X[col + c*csX]; indices >= nrows address
+ * halo rows owned by other ranks, x = ghost[(col - nrows)*k + c] (row-major receive buffer filled by
+ * the caller's neighbour exchange; NULL when the block has no halo).  Replaces
+ * NumpyMatrixOperator.apply for scipy sparse matrices (operators/numpy.py:232-237) and the
+ * "MPI-aware operator" the reference delegates to external solvers (operators/mpi.py:22-26). */
 int pmc_csr_apply(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
-                  const double *vals, const double *X, int64_t csX, double *Y, int64_t csY,
-                  int32_t k, uint32_t flags);
+                  const double *vals, const double *X, int64_t csX, const double *ghost, double *Y,
+                  int64_t csY, int32_t k, uint32_t flags);
+
+/* Halo packing: out[r*k + c] = A[idx[r] + c*csA] for a DEVICE index array (the rows a neighbour
+ * rank asked for), row-major so that one contiguous message per neighbour results. */
+int pmc_gather_rows(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n,
+                    const int64_t *idx_dev, int64_t nidx, double *out, uint32_t flags);
 
 /* Fused CSR two-form  out[i + j*ldo] = sum_r V[r + i*csV] * (M U)[r, j]  without materialising the
  * n x k product M U: row panels of M U are formed in the workspace and contracted at once.
+ * `out` must be DEVICE memory (it is accumulated panel by panel); `ghost` as in pmc_csr_apply (for U).
  * Replaces Operator.apply2 = V.inner(op.apply(U)) (operators/interface.py:79-109). */
 int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
                  const double *vals, const double *V, int64_t csV, int32_t kV, const double *U,
-                 int64_t csU, int32_t kU, double *out, int64_t ldo, uint32_t flags);
+                 int64_t csU, int32_t kU, const double *ghost, double *out, int64_t ldo,
+                 uint32_t flags);
 
 /* Roofline denominators measured on the spot: sustained FP64 tensor-core (DMMA) and DFMA
  * throughput in TFLOP/s over `ms` milliseconds of back-to-back issue on every SM. */

@@ -35,8 +35,9 @@ _CTX_FUNCS = {
     'pmc_dofs': [_P, _I64, _I32, _I64, _P, _I32, _P, _U32],
     'pmc_amax': [_P, _I64, _I32, _I64, _P, _P, _U32],
     'pmc_diag_apply': [_P, _P, _I64, _P, _I64, _I32, _I64, _U32],
-    'pmc_csr_apply': [_I64, _P, _P, _P, _P, _I64, _P, _I64, _I32, _U32],
-    'pmc_csr_gram': [_I64, _P, _P, _P, _P, _I64, _I32, _P, _I64, _I32, _P, _I64, _U32],
+    'pmc_csr_apply': [_I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _U32],
+    'pmc_gather_rows': [_P, _I64, _I32, _I64, _P, _I64, _P, _U32],
+    'pmc_csr_gram': [_I64, _P, _P, _P, _P, _I64, _I32, _P, _I64, _I32, _P, _P, _I64, _U32],
     'pmc_measure_fp64_peak': [c_int, c_double, _P],
 }
 _OTHER_FUNCS = {

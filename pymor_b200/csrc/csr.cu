@@ -13,7 +13,8 @@ constexpr int CSR_THREADS = 256;
 __global__ void __launch_bounds__(CSR_THREADS)
 csr_apply_kernel(int64_t row0, int64_t nrows, const int64_t *__restrict__ rowptr,
                  const int32_t *__restrict__ colidx, const double *__restrict__ vals,
-                 const double *__restrict__ X, int64_t csX, double *__restrict__ Y, int64_t csY, int k) {
+                 const double *__restrict__ X, int64_t csX, int64_t n_local,
+                 const double *__restrict__ ghost, double *__restrict__ Y, int64_t csY, int k) {
     const int64_t r = (int64_t)blockIdx.x * CSR_THREADS + threadIdx.x;
     if (r >= nrows) return;
     const int j0 = blockIdx.y * CJ;
@@ -21,20 +22,26 @@ csr_apply_kernel(int64_t row0, int64_t nrows, const int64_t *__restrict__ rowptr
     double acc[CJ];
 #pragma unroll
     for (int jj = 0; jj < CJ; ++jj) acc[jj] = 0.0;
-    if (j0 + CJ <= k) {
-        for (int64_t p = p0; p < p1; ++p) {
-            const double v = vals[p];
-            const double *x = X + colidx[p] + (int64_t)j0 * csX;
+    // column indices >= n_local address the halo: rows owned by other ranks, received into
+    // ghost[(col - n_local) * k + j] (row-major, one row per ghost DOF)
+    for (int64_t p = p0; p < p1; ++p) {
+        const double v = vals[p];
+        const int64_t col = colidx[p];
+        if (col < n_local) {
+            const double *x = X + col + (int64_t)j0 * csX;
+            if (j0 + CJ <= k) {
 #pragma unroll
-            for (int jj = 0; jj < CJ; ++jj) acc[jj] = fma(v, x[(int64_t)jj * csX], acc[jj]);
-        }
-    } else {
-        for (int64_t p = p0; p < p1; ++p) {
-            const double v = vals[p];
-            const double *x = X + colidx[p] + (int64_t)j0 * csX;
+                for (int jj = 0; jj < CJ; ++jj) acc[jj] = fma(v, x[(int64_t)jj * csX], acc[jj]);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < CJ; ++jj)
+                    if (j0 + jj < k) acc[jj] = fma(v, x[(int64_t)jj * csX], acc[jj]);
+            }
+        } else {
+            const double *gx = ghost + (col - n_local) * k + j0;
 #pragma unroll
             for (int jj = 0; jj < CJ; ++jj)
-                if (j0 + jj < k) acc[jj] = fma(v, x[(int64_t)jj * csX], acc[jj]);
+                if (j0 + jj < k) acc[jj] = fma(v, gx[jj], acc[jj]);
         }
     }
 #pragma unroll
@@ -42,12 +49,22 @@ csr_apply_kernel(int64_t row0, int64_t nrows, const int64_t *__restrict__ rowptr
         if (j0 + jj < k) Y[r + (int64_t)(j0 + jj) * csY] = acc[jj];
 }
 
+// halo packing: out[r * k + j] = A[idx[r] + j * csA]   (idx on the device)
+__global__ void gather_rows_kernel(const double *__restrict__ A, int64_t csA, int k,
+                                   const int64_t *__restrict__ idx, int64_t nidx, double *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nidx * k) return;
+    const int64_t r = t / k;
+    const int j = (int)(t % k);
+    out[t] = A[idx[r] + (int64_t)j * csA];
+}
+
 int launch_csr_apply(pmc_ctx *ctx, int64_t row0, int64_t nrows, const int64_t *rowptr,
-                     const int32_t *colidx, const double *vals, const double *X, int64_t csX, double *Y,
-                     int64_t csY, int k) {
+                     const int32_t *colidx, const double *vals, const double *X, int64_t csX,
+                     int64_t n_local, const double *ghost, double *Y, int64_t csY, int k) {
     dim3 grid((unsigned)ceil_div64(nrows, CSR_THREADS), (k + CJ - 1) / CJ);
-    csr_apply_kernel<<<grid, CSR_THREADS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX, Y,
-                                                          csY, k);
+    csr_apply_kernel<<<grid, CSR_THREADS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX,
+                                                          n_local, ghost, Y, csY, k);
     ctx->launches += 1;
     PMC_CHECK_CUDA(cudaGetLastError());
     return PMC_OK;
@@ -56,19 +73,20 @@ int launch_csr_apply(pmc_ctx *ctx, int64_t row0, int64_t nrows, const int64_t *r
 }  // namespace
 
 extern "C" int pmc_csr_apply(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
-                             const double *vals, const double *X, int64_t csX, double *Y, int64_t csY,
-                             int32_t k, uint32_t flags) {
+                             const double *vals, const double *X, int64_t csX, const double *ghost,
+                             double *Y, int64_t csY, int32_t k, uint32_t flags) {
     PMC_REQUIRE(ctx && nrows >= 0 && k >= 0, "bad arguments");
     if (nrows == 0 || k == 0) return pmc_after_launch(ctx, 0, flags);
     PMC_REQUIRE(rowptr && colidx && vals && X && Y, "NULL pointer");
-    int rc = launch_csr_apply(ctx, 0, nrows, rowptr, colidx, vals, X, csX, Y, csY, k);
+    int rc = launch_csr_apply(ctx, 0, nrows, rowptr, colidx, vals, X, csX, nrows, ghost, Y, csY, k);
     if (rc) return rc;
     return pmc_after_launch(ctx, 0, flags);
 }
 
 extern "C" int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
                             const double *vals, const double *V, int64_t csV, int32_t kV, const double *U,
-                            int64_t csU, int32_t kU, double *out, int64_t ldo, uint32_t flags) {
+                            int64_t csU, int32_t kU, const double *ghost, double *out, int64_t ldo,
+                            uint32_t flags) {
     PMC_REQUIRE(ctx && nrows >= 0 && kV >= 0 && kU >= 0, "bad arguments");
     if (kV == 0 || kU == 0) return pmc_after_launch(ctx, 0, flags);
     PMC_REQUIRE(out && ldo >= kV, "bad output");
@@ -100,7 +118,7 @@ extern "C" int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, 
     int first = 1;
     for (int64_t r0 = 0; r0 < nrows; r0 += PR) {
         const int64_t pr = (nrows - r0 < PR) ? nrows - r0 : PR;
-        int rc = launch_csr_apply(ctx, r0, pr, rowptr, colidx, vals, U, csU, T, PR, kU);
+        int rc = launch_csr_apply(ctx, r0, pr, rowptr, colidx, vals, U, csU, nrows, ghost, T, PR, kU);
         if (rc) return rc;
         rc = pmc_gram_impl(ctx, V + r0, csV, kV, T, PR, kU, pr, nullptr, out, ldo, gflags, gws, gws_cap,
                            first ? 0 : 1);
@@ -108,4 +126,14 @@ extern "C" int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, 
         first = 0;
     }
     return pmc_after_launch(ctx, 0, flags);
+}
+
+extern "C" int pmc_gather_rows(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n,
+                               const int64_t *idx_dev, int64_t nidx, double *out, uint32_t flags) {
+    PMC_REQUIRE(ctx && k >= 0 && n >= 0 && nidx >= 0, "bad arguments");
+    if (k == 0 || nidx == 0) return pmc_after_launch(ctx, 0, flags);
+    PMC_REQUIRE(A && idx_dev && out, "NULL pointer");
+    const int64_t total = nidx * k;
+    gather_rows_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(A, csA, k, idx_dev, nidx, out);
+    return pmc_after_launch(ctx, 1, flags);
 }

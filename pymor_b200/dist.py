@@ -29,6 +29,12 @@ class SingleRank:
     def barrier(self):
         pass
 
+    def allgather_object(self, obj):
+        return [obj]
+
+    def exchange(self, sends, recvs):
+        assert not sends and not recvs
+
     def __eq__(self, other):
         return isinstance(other, SingleRank)
 
@@ -57,6 +63,20 @@ class ProcessGroupComm:
 
     def barrier(self):
         dist.barrier(group=self.group)
+
+    def allgather_object(self, obj):
+        out = [None] * self.size
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def exchange(self, sends, recvs):
+        """Neighbour exchange: ``sends`` / ``recvs`` map peer rank -> contiguous tensor.  Point-to-point
+        (NCCL send/recv over NVLink on the GPU box, gloo in the CPU tests); every rank must call it."""
+        ops = [dist.P2POp(dist.irecv, t, p, group=self.group) for p, t in sorted(recvs.items())]
+        ops += [dist.P2POp(dist.isend, t, p, group=self.group) for p, t in sorted(sends.items())]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
 
     def __eq__(self, other):
         return isinstance(other, ProcessGroupComm) and other.group is self.group

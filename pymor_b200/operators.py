@@ -9,7 +9,8 @@ kernels so that weighted Gramians, norms and Galerkin projections never allocate
 * :class:`CudaDiagonalOperator` -- diagonal (lumped-mass / FV L2) products: the weight is applied to
   the B-fragment inside the TMA + DMMA Gram kernel resp. inside the streaming reduction.
 * :class:`CudaCsrOperator` -- sparse (FEM mass/stiffness) matrices in CSR: ``apply2`` forms row panels
-  of ``M U`` in an L2-sized scratch and contracts them at once.
+  of ``M U`` in an L2-sized scratch and contracts them at once; on row-sharded spaces the rows of
+  ``U`` owned by other ranks are fetched by a neighbour (halo) exchange first.
 """
 from __future__ import annotations
 
@@ -91,6 +92,75 @@ class CudaDiagonalOperator(Operator):
         return self
 
 
+class _ShardedCsr:
+    """This rank's row block of a sparse matrix on the device, plus the halo plan.
+
+    Columns owned by this rank are renumbered to ``[0, n_local)``; columns owned by other ranks
+    ("ghost" DOFs) to ``n_local + position`` in the sorted list of ghost indices.  Before every
+    product the ghost rows of the operand are fetched from their owners: each owner packs the rows a
+    neighbour asked for (``pmc_gather_rows``) and sends them point-to-point (NCCL over NVLink).  This
+    is the "MPI-aware operator" the reference leaves to external solvers
+    (src/pymor/operators/mpi.py:22-26)."""
+
+    def __init__(self, csr, space):
+        comm = space.comm
+        lo, n = space.offset, space.local_dim
+        hi = lo + n
+        local = sps.csr_matrix(csr[lo:hi])
+        local.sort_indices()
+        cols = local.indices.astype(np.int64)
+        mine = (cols >= lo) & (cols < hi)
+        ghosts = np.unique(cols[~mine])
+        new_cols = np.where(mine, cols - lo, n + np.searchsorted(ghosts, cols))
+        assert n + len(ghosts) < 2 ** 31
+        starts = np.concatenate((np.cumsum(space.local_dims) - space.local_dims, [space.dim]))
+        owner = np.searchsorted(starts, ghosts, side='right') - 1
+        need = {int(p): ghosts[owner == p] for p in np.unique(owner)}      # peer -> global rows I need
+        all_need = comm.allgather_object(need)
+        dev = space.device
+        self.n_ghost = len(ghosts)
+        self.recv = {}                                                     # peer -> (first ghost slot, count)
+        pos = 0
+        for p in sorted(need):
+            self.recv[p] = (pos, len(need[p]))
+            pos += len(need[p])
+        self.send = {}                                                     # peer -> device int64 local rows
+        for r, wanted in enumerate(all_need):
+            rows = wanted.get(comm.rank)
+            if r != comm.rank and rows is not None and len(rows):
+                self.send[r] = torch.from_numpy(np.ascontiguousarray(rows - lo, dtype=np.int64)).to(dev)
+        self.rowptr = torch.from_numpy(local.indptr.astype(np.int64)).to(dev)
+        self.colidx = torch.from_numpy(new_cols.astype(np.int32)).to(dev)
+        self.vals = torch.from_numpy(local.data.astype(np.float64)).to(dev)
+        self.needs_exchange = comm.size > 1 and any(len(w) for d in all_need for w in d.values())
+
+    @classmethod
+    def from_device(cls, rowptr, colidx, vals):
+        self = cls.__new__(cls)
+        self.rowptr, self.colidx, self.vals = rowptr.contiguous(), colidx.contiguous(), vals.contiguous()
+        self.n_ghost, self.recv, self.send, self.needs_exchange = 0, {}, {}, False
+        return self
+
+    def halo(self, space, ptr, cs, k):
+        """Fetch the ghost rows of the panel ``(ptr, cs, k)``; returns the (n_ghost, k) buffer or None.
+        Collective over the communicator when any rank has ghosts."""
+        if not self.needs_exchange:
+            return None
+        ghost = torch.empty((max(self.n_ghost, 1), k), dtype=torch.float64, device=space.device)
+        sends, recvs = {}, {}
+        for p, idx in self.send.items():
+            buf = torch.empty((idx.numel(), k), dtype=torch.float64, device=space.device)
+            space.ctx.call('pmc_gather_rows', ptr, cs, k, space.local_dim, idx.data_ptr(), idx.numel(),
+                           buf.data_ptr(), 0)
+            sends[p] = buf
+        for p, (first, count) in self.recv.items():
+            recvs[p] = ghost[first:first + count]
+        if space.device.type == 'cuda':
+            torch.cuda.current_stream(space.device).synchronize()   # packed buffers complete before NCCL reads
+        space.comm.exchange(sends, recvs)
+        return ghost
+
+
 class CudaCsrOperator(Operator):
     """Sparse matrix operator with the CSR arrays resident on the device.
 
@@ -98,10 +168,10 @@ class CudaCsrOperator(Operator):
     ----------
     matrix
         SciPy sparse matrix (any format; converted to CSR with int64 row pointers and int32 column
-        indices) of shape ``(space.dim, space.dim)``.
+        indices) of shape ``(space.dim, space.dim)`` -- the GLOBAL matrix; every rank keeps its row
+        block.  Couplings across shard boundaries are served by a halo exchange.
     space
-        The :class:`CudaVectorSpace` (source and range).  Sharded spaces (more than one rank) are
-        supported for block-diagonal matrices only (no halo exchange yet).
+        The :class:`CudaVectorSpace` (source and range).
     """
 
     linear = True
@@ -116,40 +186,26 @@ class CudaCsrOperator(Operator):
         self._dev_T = None
         if matrix is not None:
             assert matrix.shape == (space.dim, space.dim)
-            self._dev = self._upload(sps.csr_matrix(matrix))
+            self._dev = _ShardedCsr(sps.csr_matrix(matrix), space)
 
     @classmethod
     def from_device_csr(cls, rowptr, colidx, vals, space, name=None):
-        """Adopt CSR arrays already on the device (int64 rowptr, int32 colidx, fp64 vals)."""
+        """Adopt this rank's CSR block already on the device (int64 rowptr, int32 colidx with LOCAL
+        column numbers, fp64 vals); no halo."""
         op = cls(None, space, name=name)
         assert rowptr.dtype == torch.int64 and colidx.dtype == torch.int32 and vals.dtype == torch.float64
-        object.__setattr__(op, '_dev', (rowptr.contiguous(), colidx.contiguous(), vals.contiguous()))
+        object.__setattr__(op, '_dev', _ShardedCsr.from_device(rowptr, colidx, vals))
         return op
 
-    def _upload(self, csr):
-        space = self.space
-        lo, hi = space.offset, space.offset + space.local_dim
-        local = csr[lo:hi]
-        if space.comm.size > 1:
-            cols = local.indices
-            if cols.size and (cols.min() < lo or cols.max() >= hi):
-                raise NotImplementedError('sharded CSR operators need a halo exchange (block-diagonal only)')
-            local = sps.csr_matrix((local.data, local.indices - lo, local.indptr),
-                                   shape=(space.local_dim, space.local_dim))
-        local.sort_indices()
-        dev = space.device
-        return (torch.from_numpy(local.indptr.astype(np.int64)).to(dev),
-                torch.from_numpy(local.indices.astype(np.int32)).to(dev),
-                torch.from_numpy(local.data.astype(np.float64)).to(dev))
-
-    def _apply_csr(self, csr_dev, U):
+    def _apply_csr(self, blk, U):
         pu, csu, k, keep = U.impl._panel(U.ind)
         out = CudaVectorArrayImpl.allocate(self.space, k)
         n = self.space.local_dim
+        ghost = blk.halo(self.space, pu, csu, k) if k else None
         if k and n:
-            rowptr, colidx, vals = csr_dev
-            self.space.ctx.call('pmc_csr_apply', n, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(),
-                                pu, csu, out._ptr(0), out.ld, k, 0)
+            self.space.ctx.call('pmc_csr_apply', n, blk.rowptr.data_ptr(), blk.colidx.data_ptr(),
+                                blk.vals.data_ptr(), pu, csu, ghost.data_ptr() if ghost is not None else 0,
+                                out._ptr(0), out.ld, k, 0)
         del keep
         return CudaVectorArray(self.space, out)
 
@@ -162,7 +218,7 @@ class CudaCsrOperator(Operator):
         if self._dev_T is None:
             if self.matrix is None:
                 raise NotImplementedError('apply_adjoint needs the host matrix to build the transpose')
-            self._dev_T = self._upload(sps.csr_matrix(self.matrix.T))
+            self._dev_T = _ShardedCsr(sps.csr_matrix(self.matrix.T), self.space)
         return self._apply_csr(self._dev_T, V)
 
     def apply2(self, V, U, mu=None):
@@ -171,11 +227,13 @@ class CudaCsrOperator(Operator):
         pu, csu, ku, keep_u = U.impl._panel(U.ind)
         if kv == 0 or ku == 0:
             return np.zeros((kv, ku), order='F')
-        sp = self.space
-        out = torch.empty(kv * ku, dtype=torch.float64, device=sp.device)   # accumulated on the device
-        rowptr, colidx, vals = self._dev
-        sp.ctx.call('pmc_csr_gram', sp.local_dim, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(),
-                    pv, csv, kv, pu, csu, ku, out.data_ptr(), kv, sp.kernel_flags)
+        sp, blk = self.space, self._dev
+        ghost = blk.halo(sp, pu, csu, ku)
+        out = torch.zeros(kv * ku, dtype=torch.float64, device=sp.device)   # accumulated on the device
+        if sp.local_dim:
+            sp.ctx.call('pmc_csr_gram', sp.local_dim, blk.rowptr.data_ptr(), blk.colidx.data_ptr(),
+                        blk.vals.data_ptr(), pv, csv, kv, pu, csu, ku,
+                        ghost.data_ptr() if ghost is not None else 0, out.data_ptr(), kv, sp.kernel_flags)
         if sp.comm.size > 1:
             sp.comm.allreduce_sum_(out)
         del keep_v, keep_u

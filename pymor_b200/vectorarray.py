@@ -230,6 +230,14 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         k_other = other.len_ind(oind)
         if k_other == 0:
             return
+        if (remove_from_other and self._len == 0 and other is not self
+                and _progression(oind, other._len) == (0, 1, other._len)
+                and other._buf.shape[0] >= self._buf.shape[0] and other.ld == self.ld):
+            # moving a whole array into an empty one: adopt its buffer instead of copying
+            # (`remove_from_other` exists for exactly this, interface.py:279-282)
+            self._buf, other._buf = other._buf, self._buf
+            self._len, other._len = other._len, 0
+            return
         if other is self:
             src = self._copied(oind)
             ptr, cs, keep = src._ptr(0), src.ld, src

@@ -174,23 +174,36 @@ class EmulatedLib:
             _col(Y, csY, c, n)[:] = x[:, c]
         return PMC_OK
 
-    def _csr(self, nrows, rowptr, colidx, vals):
+    def _csr_times(self, nrows, rowptr, colidx, vals, X, csX, k, ghost):
+        """M [X; ghost] with column indices >= nrows addressing the row-major ghost buffer."""
         import scipy.sparse as sps
         rp = _vec(rowptr, nrows + 1, np.int64)
         nnz = int(rp[-1])
-        return sps.csr_matrix((_vec(vals, nnz).copy(), _vec(colidx, nnz, np.int32).copy(), rp.copy()),
-                              shape=(nrows, nrows))
+        ci = _vec(colidx, nnz, np.int32).copy()
+        nghost = int(ci.max()) + 1 - nrows if nnz and ci.max() >= nrows else 0
+        m = sps.csr_matrix((_vec(vals, nnz).copy(), ci, rp.copy()), shape=(nrows, nrows + nghost))
+        x = _panel(X, csX, k, nrows)
+        if nghost:
+            assert ghost, 'halo columns present but no ghost buffer passed'
+            x = np.vstack([x, _vec(ghost, nghost * k).reshape((nghost, k))])
+        return m @ x
 
-    def pmc_csr_apply(self, ctx, nrows, rowptr, colidx, vals, X, csX, Y, csY, k, flags):
+    def pmc_csr_apply(self, ctx, nrows, rowptr, colidx, vals, X, csX, ghost, Y, csY, k, flags):
         self._note('pmc_csr_apply')
-        y = self._csr(nrows, rowptr, colidx, vals) @ _panel(X, csX, k, nrows)
+        y = self._csr_times(nrows, rowptr, colidx, vals, X, csX, k, ghost)
         for c in range(k):
             _col(Y, csY, c, nrows)[:] = y[:, c]
         return PMC_OK
 
-    def pmc_csr_gram(self, ctx, nrows, rowptr, colidx, vals, V, csV, kV, U, csU, kU, out, ldo, flags):
+    def pmc_gather_rows(self, ctx, A, csA, k, n, idx, nidx, out, flags):
+        self._note('pmc_gather_rows')
+        ix = _vec(idx, nidx, np.int64)
+        _vec(out, nidx * k).reshape((nidx, k))[:] = _panel(A, csA, k, n)[ix, :]
+        return PMC_OK
+
+    def pmc_csr_gram(self, ctx, nrows, rowptr, colidx, vals, V, csV, kV, U, csU, kU, ghost, out, ldo, flags):
         self._note('pmc_csr_gram')
-        g = _panel(V, csV, kV, nrows).T @ (self._csr(nrows, rowptr, colidx, vals) @ _panel(U, csU, kU, nrows))
+        g = _panel(V, csV, kV, nrows).T @ self._csr_times(nrows, rowptr, colidx, vals, U, csU, kU, ghost)
         o = _vec(out, ldo * kU).reshape((ldo, kU), order='F')
         o[:kV, :] = g
         return PMC_OK

@@ -24,7 +24,7 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=10_000_000)
+    ap.add_argument('--dofs', dest='n', type=int, default=10_000_000)
     ap.add_argument('--k', type=int, default=256)
     ap.add_argument('--cpu-n', type=int, default=0, help='also time the oracle on this many rows')
     args = ap.parse_args()
