@@ -26,6 +26,11 @@ from pathlib import Path
 
 # one 74.5 GiB panel next to another: let the caching allocator remap instead of fragmenting
 os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
+# torchrun pins every rank to ONE host thread by default; the k x k eigensolve stays on the host, so give
+# each rank its share of the cores instead (must happen before NumPy/OpenBLAS is loaded)
+if int(os.environ.get('WORLD_SIZE', '1')) > 1 and os.environ.get('OMP_NUM_THREADS', '1') == '1':
+    _share = max(1, (os.cpu_count() or 1) // int(os.environ.get('LOCAL_WORLD_SIZE', os.environ['WORLD_SIZE'])))
+    os.environ['OMP_NUM_THREADS'] = os.environ['OPENBLAS_NUM_THREADS'] = str(_share)
 
 import numpy as np  # noqa: E402
 

@@ -63,6 +63,12 @@ int pmc_ctx_sync(pmc_ctx *ctx);
 int pmc_ctx_sm_count(pmc_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t pmc_ctx_launch_count(pmc_ctx *ctx);
+/* Pin caller-owned host memory (a shared-memory segment common to the ranks of one box) so that
+ * reduction kernels can write their tiny partial results straight into it; *dev_ptr_out is the address
+ * to pass as `out`.  The ranks then sum the partials on the host -- the replacement for the
+ * Gather-to-root + host sum of vectorarrays/mpi.py:394-416 when the payload is a few doubles. */
+int pmc_host_register(pmc_ctx *ctx, void *host_ptr, size_t bytes, void **dev_ptr_out);
+int pmc_host_unregister(pmc_ctx *ctx, void *host_ptr);
 
 /* inner / gramian / apply2 with a diagonal product.
  * out[i + j*ldo] = sum_d A[d + i*csA] * w[d] * B[d + j*csB]   (w == NULL: Euclidean)

@@ -39,6 +39,8 @@ _CTX_FUNCS = {
     'pmc_gather_rows': [_P, _I64, _I32, _I64, _P, _I64, _P, _U32],
     'pmc_csr_gram': [_I64, _P, _P, _P, _P, _I64, _I32, _P, _I64, _I32, _P, _P, _I64, _U32],
     'pmc_measure_fp64_peak': [c_int, c_double, _P],
+    'pmc_host_register': [_P, c_size_t, ctypes.POINTER(_P)],
+    'pmc_host_unregister': [_P],
 }
 _OTHER_FUNCS = {
     'pmc_version': ([], c_int),
@@ -161,6 +163,14 @@ class DeviceContext:
     @property
     def launch_count(self):
         return int(self.lib.pmc_ctx_launch_count(self.handle))
+
+    def register_host(self, host_ptr, nbytes):
+        """Pin caller-owned host memory; returns the address kernels may write to."""
+        out = _P()
+        rc = self.lib.pmc_host_register(self.handle, host_ptr, nbytes, ctypes.byref(out))
+        if rc != PMC_OK:
+            raise PmcError(f'pmc_host_register failed: {self._err()}')
+        return int(out.value)
 
     def measure_fp64_peak(self, use_dmma=True, ms=200.0):
         out = np.zeros(1)

@@ -116,3 +116,21 @@ int pmc_encode_tmap_f64(pmc_ctx *ctx, CUtensorMap *tm, const void *base, int ran
     }
     return PMC_OK;
 }
+
+// Pin caller-owned host memory (e.g. a POSIX shared-memory segment shared by the ranks of one box) and
+// return the address kernels can write to.  Used for the host-side sum of tiny per-rank partials.
+extern "C" int pmc_host_register(pmc_ctx *ctx, void *host_ptr, size_t bytes, void **dev_ptr_out) {
+    PMC_REQUIRE(ctx && host_ptr && bytes > 0 && dev_ptr_out, "bad arguments");
+    PMC_CHECK_CUDA(cudaSetDevice(ctx->device));
+    PMC_CHECK_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    void *d = nullptr;
+    PMC_CHECK_CUDA(cudaHostGetDevicePointer(&d, host_ptr, 0));
+    *dev_ptr_out = d;
+    return PMC_OK;
+}
+
+extern "C" int pmc_host_unregister(pmc_ctx *ctx, void *host_ptr) {
+    PMC_REQUIRE(ctx && host_ptr, "bad arguments");
+    PMC_CHECK_CUDA(cudaHostUnregister(host_ptr));
+    return PMC_OK;
+}

@@ -191,8 +191,9 @@ lincomb_simple_kernel(const double *__restrict__ A, int64_t csA, int k, int64_t 
         }
         __syncthreads();
         if (d < n) {
+#pragma unroll 4
             for (int ii = 0; ii < kc; ++ii) {
-                const double a = A[(int64_t)(i0 + ii) * csA + d];
+                const double a = ld_stream1(A + (int64_t)(i0 + ii) * csA + d);
 #pragma unroll
                 for (int jj = 0; jj < SJ; ++jj) acc[jj] = fma(a, Cs[jj * S_KC + ii], acc[jj]);
             }

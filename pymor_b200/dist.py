@@ -101,3 +101,66 @@ def merge_amax(inds, vals):
     win = np.argmax(vals, axis=0)
     cols = np.arange(vals.shape[1])
     return inds[win, cols], vals[win, cols]
+
+
+class SharedHostReducer:
+    """Sum of tiny per-rank partial results through a pinned shared-memory segment.
+
+    ``pairwise_inner`` / ``norm`` inside Gram-Schmidt return one double that the HOST needs (it drives
+    the control flow and fills ``R``).  Going device -> NCCL all-reduce -> device -> host costs several
+    launch/sync latencies per pair-step; the reference's own MPI path does a ``Gather`` to rank 0 plus a
+    host sum (src/pymor/vectorarrays/mpi.py:394-416).  Here every rank's reduction kernel writes its
+    partial straight into its slot of a POSIX shared-memory segment that all ranks of the box have
+    pinned (``cudaHostRegister``); after its own stream sync a rank publishes a sequence number, spins
+    until the other slots carry the same number and adds the slots in rank order -- every rank gets the
+    bitwise identical sum, with no collective launch.  Two slot generations (parity of the sequence
+    number) make it safe for a fast rank to start the next reduction while a slow one still reads.
+    """
+
+    HEADER = 8          # doubles reserved per slot for the sequence number (64-byte aligned payload)
+
+    def __init__(self, comm, ctx, capacity=2048):
+        from multiprocessing import shared_memory
+        self.comm, self.ctx, self.capacity = comm, ctx, int(capacity)
+        self.slot = self.HEADER + self.capacity
+        nbytes = comm.size * 2 * self.slot * 8
+        name = None
+        if comm.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            np.ndarray((nbytes // 8,), dtype=np.float64, buffer=self._shm.buf)[:] = 0.0
+            name = self._shm.name
+        name = comm.allgather_object(name)[0]
+        if comm.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=name)
+        self._data = np.ndarray((comm.size, 2, self.slot), dtype=np.float64, buffer=self._shm.buf)
+        self._seqs = self._data.view(np.int64)
+        self._host_ptr = self._data.ctypes.data
+        self._dev_ptr = ctx.register_host(self._host_ptr, nbytes)
+        self._seq = 0
+        comm.barrier()
+        if comm.rank == 0:
+            self._shm.unlink()          # the mapping stays alive in every rank; the name goes away
+
+    def target(self):
+        """Device-accessible address of this rank's payload for the NEXT reduction."""
+        gen = (self._seq + 1) & 1
+        return self._dev_ptr + ((self.comm.rank * 2 + gen) * self.slot + self.HEADER) * 8
+
+    def finish(self, count, timeout=120.0):
+        """Call after the kernel's stream has been synchronised: publish, wait for the peers, sum."""
+        import time
+        self._seq += 1
+        seq, gen = self._seq, self._seq & 1
+        self._seqs[self.comm.rank, gen, 0] = seq
+        total = np.zeros(count)
+        deadline = None
+        for r in range(self.comm.size):
+            spins = 0
+            while self._seqs[r, gen, 0] < seq:
+                spins += 1
+                if spins & 0xffff == 0:
+                    deadline = deadline or time.monotonic() + timeout
+                    if time.monotonic() > deadline:
+                        raise RuntimeError(f'rank {self.comm.rank}: timed out waiting for rank {r} in host reduction')
+            total += self._data[r, gen, self.HEADER:self.HEADER + count]
+        return total

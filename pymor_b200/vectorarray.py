@@ -16,6 +16,7 @@ contract tests tolerate this for backends, src/pymortests/vectorarray.py:66-69).
 """
 from __future__ import annotations
 
+import os
 from numbers import Number
 
 import numpy as np
@@ -27,6 +28,19 @@ from pymor_b200.dist import SingleRank, merge_amax, partition
 from pymor_b200.interface import HAVE_PYMOR, VectorArray, VectorArrayImpl, VectorSpace, create_random_values
 
 _ALIGN = 16  # doubles
+_HOST_REDUCE_MAX = 2048  # sharded reductions of at most this many doubles are summed on the host
+_SKINNY = 4  # inner products with at most this many vectors on one side use the streaming kernel
+
+
+class _RawTarget:
+    """A bare device-accessible address standing in for a tensor as reduction output."""
+    __slots__ = ('ptr',)
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def data_ptr(self):
+        return self.ptr
 
 
 def _round_up(a, b):
@@ -314,6 +328,26 @@ class CudaVectorArrayImpl(VectorArrayImpl):
             return np.zeros((ka, kb), order='F')
         sp = self.space
         out, flags = sp.reduction_target(ka * kb)
+        if min(ka, kb) <= _SKINNY and not sp.kernel_flags:
+            # skinny products (projection of a right-hand side, Gramian of a few vectors) are
+            # HBM-bound: stream the wide panel once per narrow column through the reduction kernel,
+            # the narrow column broadcast (column stride 0) and served from L2
+            last = min(ka, kb) - 1
+            for c in range(last + 1):
+                f = flags if c == last else 0
+                if kb <= ka:      # column c of the result: <a_i, b_c> for all i
+                    sp.ctx.call('pmc_pairwise_inner', pa, csa, pb + 8 * c * csb, 0, ka, self.n, weight_ptr,
+                                out.data_ptr() + 8 * c * ka, f)
+                else:             # row c of the result, written as a contiguous scratch row
+                    sp.ctx.call('pmc_pairwise_inner', pa + 8 * c * csa, 0, pb, csb, kb, self.n, weight_ptr,
+                                out.data_ptr() + 8 * c * kb, f)
+            res = sp.reduction_result(out, ka * kb)
+            res = res.reshape((ka, kb), order='F') if kb <= ka else np.asfortranarray(res.reshape((ka, kb)))
+            if symmetric:
+                low = np.tril_indices(ka, -1)
+                res[low[1], low[0]] = res[low]          # bitwise symmetric like the SYRK path
+            del keep_a, keep_b
+            return res
         if symmetric:
             flags |= PMC_SYMMETRIC
         sp.ctx.call('pmc_gram', pa, csa, ka, pb, csb, kb, self.n, weight_ptr, out.data_ptr(), ka,
@@ -480,6 +514,8 @@ class CudaVectorSpace(VectorSpace):
         self._offset = int(offsets[self._comm.rank])
         self._ld = max(_round_up(self._local_dim, _ALIGN), _ALIGN)
         self._red_dev = None
+        self._host_reducer = None
+        self._host_reduce_enabled = os.environ.get('PMC_NO_HOST_REDUCE', '0') != '1'
         self._kernel_flags = 0
         self._host_np = None
 
@@ -501,11 +537,19 @@ class CudaVectorSpace(VectorSpace):
     def reduction_target(self, count):
         if self._comm.size == 1:
             return self._ctx.host_f64(count), PMC_SYNC
+        if count <= _HOST_REDUCE_MAX and self._host_reduce_enabled:
+            # a handful of doubles the host needs anyway: per-rank partials meet in pinned shared memory
+            if self._host_reducer is None:
+                from pymor_b200.dist import SharedHostReducer
+                self._host_reducer = SharedHostReducer(self._comm, self._ctx, _HOST_REDUCE_MAX)
+            return _RawTarget(self._host_reducer.target()), PMC_SYNC
         if self._red_dev is None or self._red_dev.numel() < count:
             self._red_dev = torch.empty(max(int(count), 4096), dtype=torch.float64, device=self.device)
         return self._red_dev, 0
 
     def reduction_result(self, buf, count):
+        if type(buf) is _RawTarget:
+            return self._host_reducer.finish(count)
         if self._comm.size == 1:
             host = self._host_np
             if host is None or host[0] is not buf:

@@ -69,6 +69,13 @@ class EmulatedLib:
     def pmc_ctx_launch_count(self, ctx):
         return self.launches
 
+    def pmc_host_register(self, ctx, host_ptr, nbytes, out):
+        out._obj.value = int(host_ptr)
+        return PMC_OK
+
+    def pmc_host_unregister(self, ctx, host_ptr):
+        return PMC_OK
+
     def _note(self, name):
         self.launches += 1
         self.calls.append(name)

@@ -105,3 +105,42 @@ def test_shifted_chol_qr_next_row_N1():
     Qc, Rc = shifted_chol_qr(csp.from_numpy(A), product=cprod, return_R=True)
     np.testing.assert_allclose(Rc, Rn, rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(Qc.to_numpy(), Qn.to_numpy(), atol=1e-9)
+
+
+def test_hapod_next_row_N3():
+    """pyMOR's incremental and distributed HAPOD: every tree node is a `pod` call on the backend."""
+    from pymor.algorithms.hapod import dist_vectorarray_hapod, inc_vectorarray_hapod
+    A, nsp, csp, nprod, cprod = make(180, 40, 7, 'diag')
+    rng = np.random.default_rng(8)
+    A = np.asfortranarray((rng.standard_normal((180, 6)) @ rng.standard_normal((6, 40))) + 1e-3 * A)
+    for fn, arg in ((inc_vectorarray_hapod, 4), (dist_vectorarray_hapod, 4)):
+        mn, sn, cn = fn(arg, nsp.from_numpy(A.copy()), 1e-2, 0.75, product=nprod)
+        mc, sc, cc = fn(arg, csp.from_numpy(A), 1e-2, 0.75, product=cprod)
+        assert cn == cc and len(mn) == len(mc)
+        np.testing.assert_allclose(sc, sn, rtol=1e-8)
+        G = nsp.from_numpy(mc.to_numpy()).inner(mn, nprod)
+        np.testing.assert_allclose(np.abs(np.linalg.svd(G, compute_uv=False)), 1.0, atol=1e-7)
+
+
+def test_randomized_range_finder_next_row_N2():
+    """pyMOR's RandomizedRangeFinder / randomized_svd with a CUDA CSR operator as `A`: exercises
+    Operator.apply / apply_adjoint, space.random (pyMOR's global RNG -> identical samples) and GS."""
+    from pymor.algorithms.rand_la import RandomizedRangeFinder, randomized_svd
+    from pymor.tools.random import new_rng
+    dim = 140
+    rng = np.random.default_rng(9)
+    L, Rr = rng.standard_normal((dim, 5)), rng.standard_normal((5, dim))
+    M = sps.csr_matrix(L @ Rr) + 1e-6 * sps.eye(dim)
+    nsp, csp = NumpyVectorSpace(dim), CudaVectorSpace(dim, device=DEVICE)
+    on, oc = NumpyMatrixOperator(M), CudaCsrOperator(M, csp)
+    with new_rng(3):
+        Qn = RandomizedRangeFinder(on, power_iterations=1).find_range(basis_size=8)
+    with new_rng(3):
+        Qc = RandomizedRangeFinder(oc, power_iterations=1).find_range(basis_size=8)
+    np.testing.assert_allclose(Qc.to_numpy(), Qn.to_numpy(), atol=1e-8)
+    with new_rng(4):
+        Un, sn, Vn = randomized_svd(on, 5)
+    with new_rng(4):
+        Uc, sc, Vc = randomized_svd(oc, 5)
+    np.testing.assert_allclose(sc, sn, rtol=1e-8)
+    np.testing.assert_allclose(np.abs(nsp.from_numpy(Uc.to_numpy()).inner(Un)), np.eye(5), atol=1e-6)
