@@ -172,6 +172,9 @@ class DeviceContext:
             raise PmcError(f'pmc_host_register failed: {self._err()}')
         return int(out.value)
 
+    def unregister_host(self, host_ptr):
+        self.lib.pmc_host_unregister(self.handle, host_ptr)
+
     def measure_fp64_peak(self, use_dmma=True, ms=200.0):
         out = np.zeros(1)
         self.call('pmc_measure_fp64_peak', int(bool(use_dmma)), float(ms), out.ctypes.data)

@@ -138,8 +138,31 @@ class SharedHostReducer:
         self._dev_ptr = ctx.register_host(self._host_ptr, nbytes)
         self._seq = 0
         comm.barrier()
+        from multiprocessing import resource_tracker
+        try:                            # every rank keeps its mapping; the name goes away right now
+            resource_tracker.unregister(self._shm._name, 'shared_memory')
+        except Exception:
+            pass
         if comm.rank == 0:
-            self._shm.unlink()          # the mapping stays alive in every rank; the name goes away
+            try:
+                import os
+                os.unlink('/dev/shm/' + self._shm.name.lstrip('/'))
+            except OSError:
+                pass
+
+    def close(self):
+        if self._shm is None:
+            return
+        try:
+            self.ctx.unregister_host(self._host_ptr)
+        except Exception:
+            pass
+        self._data = self._seqs = None
+        try:
+            self._shm.close()
+        except Exception:
+            pass
+        self._shm = None
 
     def target(self):
         """Device-accessible address of this rank's payload for the NEXT reduction."""
@@ -164,3 +187,26 @@ class SharedHostReducer:
                         raise RuntimeError(f'rank {self.comm.rank}: timed out waiting for rank {r} in host reduction')
             total += self._data[r, gen, self.HEADER:self.HEADER + count]
         return total
+
+
+_reducers = {}
+
+
+def get_host_reducer(comm, ctx, capacity):
+    """One reducer per (process group, device): spaces come and go, the pinned segment stays."""
+    key = (id(getattr(comm, 'group', None)), str(ctx.device))
+    red = _reducers.get(key)
+    if red is None:
+        red = _reducers[key] = SharedHostReducer(comm, ctx, capacity)
+    return red
+
+
+def _close_reducers():
+    for red in _reducers.values():
+        red.close()
+    _reducers.clear()
+
+
+import atexit  # noqa: E402
+
+atexit.register(_close_reducers)

@@ -540,8 +540,8 @@ class CudaVectorSpace(VectorSpace):
         if count <= _HOST_REDUCE_MAX and self._host_reduce_enabled:
             # a handful of doubles the host needs anyway: per-rank partials meet in pinned shared memory
             if self._host_reducer is None:
-                from pymor_b200.dist import SharedHostReducer
-                self._host_reducer = SharedHostReducer(self._comm, self._ctx, _HOST_REDUCE_MAX)
+                from pymor_b200.dist import get_host_reducer
+                self._host_reducer = get_host_reducer(self._comm, self._ctx, _HOST_REDUCE_MAX)
             return _RawTarget(self._host_reducer.target()), PMC_SYNC
         if self._red_dev is None or self._red_dev.numel() < count:
             self._red_dev = torch.empty(max(int(count), 4096), dtype=torch.float64, device=self.device)
