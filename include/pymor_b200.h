@@ -106,6 +106,13 @@ int pmc_norm2(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n, 
 int pmc_axpy(pmc_ctx *ctx, double *Y, int64_t csY, const double *X, int64_t csX, int32_t k,
              int64_t n, const double *alpha, int32_t n_alpha, uint32_t flags);
 
+/* Fused Gram-Schmidt step on single vectors: Y += alpha[0]*X, then out[0] = sum_d Q[d]*w[d]*Y[d]
+ * (Q == NULL: out[0] = sum_d w[d]*Y[d]^2) in one pass.  Bitwise identical to pmc_axpy followed by
+ * pmc_pairwise_inner(Q, Y) / pmc_norm2(Y); the host layer uses it to merge `v.axpy(-p, q_j)` with the
+ * following `q_{j+1}.pairwise_inner(v)` / `v.norm()` of gram_schmidt.py:84-91. */
+int pmc_axpy_dot(pmc_ctx *ctx, double *Y, const double *X, const double *alpha, const double *Q,
+                 int64_t n, const double *w, double *out, uint32_t flags);
+
 /* scal: Y[:, c] *= alpha[c or 0].  Replaces NumpyVectorArrayImpl.scal (numpy.py:85-100). */
 int pmc_scal(pmc_ctx *ctx, double *Y, int64_t csY, int32_t k, int64_t n, const double *alpha,
              int32_t n_alpha, uint32_t flags);

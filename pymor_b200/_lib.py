@@ -6,6 +6,7 @@ a :class:`DeviceContext` raises.  All pointers cross the boundary as plain integ
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_double, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 
@@ -30,6 +31,7 @@ _CTX_FUNCS = {
     'pmc_norm2': [_P, _I64, _I32, _I64, _P, _P, _U32],
     'pmc_axpy': [_P, _I64, _P, _I64, _I32, _I64, _P, _I32, _U32],
     'pmc_scal': [_P, _I64, _I32, _I64, _P, _I32, _U32],
+    'pmc_axpy_dot': [_P, _P, _P, _P, _I64, _P, _P, _U32],
     'pmc_copy': [_P, _I64, _P, _I64, _I32, _I64, _U32],
     'pmc_gather_cols': [_P, _I64, _P, _I64, _P, _I32, _I64, _U32],
     'pmc_dofs': [_P, _I64, _I32, _I64, _P, _I32, _P, _U32],
@@ -98,6 +100,7 @@ class DeviceContext:
 
     def __init__(self, device):
         self.lib = load_library()
+        self._fns = {}
         self.device = torch.device(device)
         on_cuda = self.device.type == 'cuda'
         if on_cuda:
@@ -114,6 +117,12 @@ class DeviceContext:
         self._pin = on_cuda
         self._ws = None
         self.ensure_workspace(64 << 20)
+        # deferred single-vector axpy (see CudaVectorArrayImpl.axpy): at most one per device, flushed by
+        # any other operation; merged with the next dot/norm on its target by pmc_axpy_dot
+        self.pending = None
+        self.fuse_axpy = os.environ.get('PMC_NO_FUSE_AXPY', '0') != '1'
+        self.scalar = np.zeros(1)                      # staging for scalar coefficients (read at launch)
+        self.scalar_ptr = self.scalar.ctypes.data
         self._host_f64 = torch.empty(1 << 16, dtype=torch.float64, pin_memory=self._pin)
         self._host_i64 = torch.empty(1 << 12, dtype=torch.int64, pin_memory=self._pin)
 
@@ -131,7 +140,9 @@ class DeviceContext:
 
     def call(self, name, *args):
         """Invoke ``name(ctx, *args)``; grows the workspace and retries on PMC_ERR_WORKSPACE."""
-        fn = getattr(self.lib, name)
+        fn = self._fns.get(name)
+        if fn is None:
+            fn = self._fns[name] = getattr(self.lib, name)
         rc = fn(self.handle, *args)
         if rc == PMC_ERR_WORKSPACE:
             need = int(self.lib.pmc_ctx_workspace_needed(self.handle))
@@ -139,6 +150,16 @@ class DeviceContext:
             rc = fn(self.handle, *args)
         if rc != PMC_OK:
             raise PmcError(f'{name} failed ({rc}): {self._err()}')
+
+    def flush(self):
+        """Launch the deferred axpy, if any."""
+        pend = self.pending
+        if pend is not None:
+            self.pending = None
+            timpl, tcol, alpha, ximpl, xcol = pend
+            self.scalar[0] = alpha
+            self.call('pmc_axpy', timpl._ptr(tcol), timpl.ld, ximpl._ptr(xcol), ximpl.ld, 1, timpl.n,
+                      self.scalar_ptr, 1, 0)
 
     def host_f64(self, count):
         """Pinned (device-writable) host buffer of at least ``count`` doubles."""
@@ -152,6 +173,7 @@ class DeviceContext:
         return self._host_i64
 
     def sync(self):
+        self.flush()
         rc = self.lib.pmc_ctx_sync(self.handle)
         if rc != PMC_OK:
             raise PmcError(self._err())

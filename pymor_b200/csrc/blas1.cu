@@ -137,6 +137,93 @@ int launch_reduce(pmc_ctx *ctx, const double *A, int64_t csA, const double *B, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused Gram-Schmidt step:  y += alpha * x ;  out = sum_d q[d] * w[d] * y_new[d]   (q == y: norm2)
+// One pass instead of an axpy launch followed by a reduction launch: the host layer defers the
+// axpy of `v.axpy(-p, q_j)` until the next `q_{j+1}.pairwise_inner(v)` / `v.norm()` arrives.
+// Same arithmetic and the same summation order as the two separate kernels (bitwise identical).
+// ---------------------------------------------------------------------------------------------
+template <bool NORM, bool WEIGHTED>
+__global__ void __launch_bounds__(TPB)
+axpy_dot_kernel(double *__restrict__ y, const double *__restrict__ x, double alpha,
+                const double *__restrict__ q, const double *__restrict__ w, int64_t n,
+                double *__restrict__ partials, unsigned int *__restrict__ tickets,
+                double *__restrict__ out, int keep) {
+    const int bx = gridDim.x;
+    const uint64_t pol_hot = l2_policy(keep ? 2 : 0), pol_cold = l2_policy(keep ? 1 : 0);
+    double acc[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc[u] = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * CHUNK; base < n; base += (int64_t)bx * CHUNK) {
+        if (base + CHUNK <= n) {
+            double2 xv[UNROLL], yv[UNROLL], qv[UNROLL], wv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t i = base + 2 * (threadIdx.x + u * TPB);
+                xv[u] = ld_hint2_nc(x + i, pol_cold);
+                yv[u] = ld_hint2(y + i, pol_hot);
+                if (!NORM) qv[u] = ld_hint2_nc(q + i, pol_cold);
+                if (WEIGHTED) wv[u] = ld_hint2_nc(w + i, pol_cold);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t i = base + 2 * (threadIdx.x + u * TPB);
+                double2 r;
+                r.x = fma(alpha, xv[u].x, yv[u].x);
+                r.y = fma(alpha, xv[u].y, yv[u].y);
+                st_hint2(y + i, r, pol_hot);
+                double2 a = NORM ? r : qv[u];
+                double2 b = r;
+                if (WEIGHTED) { b.x *= wv[u].x; b.y *= wv[u].y; }
+                acc[u] = fma(a.x, b.x, acc[u]);
+                acc[u] = fma(a.y, b.y, acc[u]);
+            }
+        } else {
+            const int64_t end = n;
+            for (int64_t i = base + threadIdx.x; i < end; i += TPB) {
+                const double r = fma(alpha, x[i], y[i]);
+                y[i] = r;
+                const double a = NORM ? r : q[i];
+                double b = r;
+                if (WEIGHTED) b *= w[i];
+                acc[0] = fma(a, b, acc[0]);
+            }
+        }
+    }
+    double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    s = warp_sum(s);
+    __shared__ double wsum[TPB / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < TPB / 32; ++i) t += wsum[i];
+        if (bx == 1) {
+            out[0] = t;
+            is_last = false;
+        } else {
+            partials[blockIdx.x] = t;
+            __threadfence();
+            is_last = (atomicAdd(&tickets[0], 1u) == (unsigned int)bx - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last && warp == 0) {
+        __threadfence();
+        double t = 0.0;
+        const volatile double *p = partials;
+        for (int i = lane; i < bx; i += 32) t += p[i];
+        t = warp_sum(t);
+        if (lane == 0) {
+            out[0] = t;
+            tickets[0] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // elementwise column kernels
 // ---------------------------------------------------------------------------------------------
 enum { OP_AXPY = 0, OP_SCAL = 1, OP_COPY = 2, OP_DIAG = 3 };
@@ -444,4 +531,29 @@ extern "C" int pmc_amax(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, i
         ++launches;
     }
     return pmc_after_launch(ctx, launches, flags);
+}
+
+extern "C" int pmc_axpy_dot(pmc_ctx *ctx, double *Y, const double *X, const double *alpha, const double *Q,
+                            int64_t n, const double *w, double *out, uint32_t flags) {
+    PMC_REQUIRE(ctx && n >= 0 && alpha && out, "bad arguments");
+    if (n == 0) {
+        PMC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), ctx->stream));
+        return pmc_after_launch(ctx, 0, flags);
+    }
+    PMC_REQUIRE(Y && X, "NULL vector");
+    const bool vec = aligned16(Y) && aligned16(X) && (!Q || aligned16(Q)) && (!w || aligned16(w));
+    if (!vec) {   // misaligned vectors: same result from the two separate kernels
+        int rc = pmc_axpy(ctx, Y, 0, X, 0, 1, n, alpha, 1, 0);
+        if (rc) return rc;
+        return Q ? pmc_pairwise_inner(ctx, Q, 0, Y, 0, 1, n, w, out, flags) : pmc_norm2(ctx, Y, 0, 1, n, w, out, flags);
+    }
+    const int bx = blocks_per_col(ctx, n, 1, 8);
+    const int keep = (ctx->l2_keep && n * 8 <= L2_KEEP_BYTES) ? 1 : 0;
+#define PMC_LAUNCH_AD(NM, WT)                                                                            \
+    axpy_dot_kernel<NM, WT><<<bx, TPB, 0, ctx->stream>>>(Y, X, alpha[0], Q, w, n, ctx->partials, ctx->tickets, \
+                                                        out, keep)
+    if (Q) { if (w) PMC_LAUNCH_AD(false, true); else PMC_LAUNCH_AD(false, false); }
+    else   { if (w) PMC_LAUNCH_AD(true, true); else PMC_LAUNCH_AD(true, false); }
+#undef PMC_LAUNCH_AD
+    return pmc_after_launch(ctx, 1, flags);
 }

@@ -309,10 +309,12 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
     p.tiles_n = (kB + T - 1) / T;
     p.ntiles = sym ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
 
-    // split-n: aim at ~4 full waves of CTAs (1 CTA/SM for the DMMA kernel), each item >= 64 steps
+    // split-n: aim at ~gram_waves full waves of CTAs (1 CTA/SM for the DMMA kernel), each item >= 64 steps
     const int64_t steps = ceil_div64(n, rows_q);
     const int ctas_per_wave = ctx->sm_count * (tma_ok ? 1 : 4);
-    int64_t nsplit = ceil_div64((int64_t)4 * ctas_per_wave, p.ntiles);
+    // items differ in cost (diagonal SYRK tiles are cheaper), so the tail of the last wave matters:
+    // more, smaller items keep it short (env PMC_GRAM_WAVES for tuning)
+    int64_t nsplit = ceil_div64((int64_t)ctx->gram_waves * ctas_per_wave, p.ntiles);
     const int64_t max_split = steps / 64 > 0 ? steps / 64 : 1;
     if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;

@@ -28,6 +28,7 @@ from pymor_b200.dist import SingleRank, merge_amax, partition
 from pymor_b200.interface import HAVE_PYMOR, VectorArray, VectorArrayImpl, VectorSpace, create_random_values
 
 _ALIGN = 16  # doubles
+_FLOAT_TYPES = (float, np.float64, int)
 _HOST_REDUCE_MAX = 2048  # sharded reductions of at most this many doubles are summed on the host
 _SKINNY = 4  # inner products with at most this many vectors on one side use the streaming kernel
 
@@ -145,9 +146,20 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         buf = alloc((cap, space.ld), dtype=torch.float64, device=space.device)
         return cls(space, buf, count)
 
+    # the buffer's address and leading dimension are cached: they are read on every kernel call
+    @property
+    def _buf(self):
+        return self._buf_t
+
+    @_buf.setter
+    def _buf(self, t):
+        self._buf_t = t
+        self._base = t.data_ptr()
+        self._ld = t.stride(0)
+
     @property
     def ld(self):
-        return self._buf.stride(0)
+        return self._ld
 
     @property
     def n(self):
@@ -157,11 +169,12 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return self._len
 
     def _ptr(self, col=0):
-        return self._buf.data_ptr() + col * self._buf.stride(0) * 8
+        return self._base + col * self._ld * 8
 
     def _panel(self, ind):
         """(ptr, column stride, count, keepalive) of a READ-ONLY panel; arbitrary index lists are
         gathered into a temporary (numpy.py:21 fancy indexing does the same)."""
+        self.space.ctx.flush()
         prog = _progression(ind, self._len)
         if prog is not None:
             start, step, count = prog
@@ -170,6 +183,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return tmp._ptr(0), tmp.ld, tmp._len, tmp
 
     def _gathered(self, cols, reserve=0):
+        self.space.ctx.flush()
         new = CudaVectorArrayImpl.allocate(self.space, len(cols), reserve)
         if len(cols) and self.n:
             idx = np.ascontiguousarray(cols, dtype=np.int64)
@@ -178,6 +192,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return new
 
     def _copied(self, ind, reserve=0):
+        self.space.ctx.flush()
         prog = _progression(ind, self._len)
         if prog is None:
             return self._gathered(_columns(ind, self._len), reserve)
@@ -202,6 +217,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return CudaVectorArrayImpl.allocate(self.space, self.len_ind(ind), zero=True)
 
     def to_numpy(self, ensure_copy, ind):
+        self.space.ctx.flush()
         prog = _progression(ind, self._len)
         if prog is not None and prog[1] == 1:
             block = self._buf[prog[0]:prog[0] + prog[2], :self.n]
@@ -219,6 +235,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return host.T
 
     def delete(self, ind):
+        self.space.ctx.flush()
         if ind is None:
             self._len = 0
             return
@@ -241,6 +258,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         self._len = len(keep)
 
     def append(self, other, remove_from_other, oind):
+        self.space.ctx.flush()
         k_other = other.len_ind(oind)
         if k_other == 0:
             return
@@ -273,6 +291,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
             other.delete(oind)
 
     def scal(self, alpha, ind):
+        self.space.ctx.flush()
         cols = _columns(ind, self._len)
         if len(cols) == 0 or self.n == 0:
             _real_scalars(alpha, len(cols))
@@ -293,6 +312,25 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return _runs(list(cols))
 
     def axpy(self, alpha, x, ind, xind):
+        # fast path of the Gram-Schmidt inner step: one vector += scalar * another vector, both
+        # addressed by the unit slices ``A[i]`` / ``A[j]`` produce (interface.py:219-223)
+        if (type(ind) is slice and type(xind) is slice and type(alpha) in _FLOAT_TYPES
+                and ind.step in (None, 1) and xind.step in (None, 1)
+                and ind.stop is not None and xind.stop is not None
+                and ind.stop - ind.start == 1 and xind.stop - xind.start == 1
+                and 0 <= ind.start < self._len and 0 <= xind.start < x._len and self.n
+                and not (x._buf is self._buf and ind.start == xind.start)):
+            ctx = self.space.ctx
+            ctx.flush()
+            if ctx.fuse_axpy:
+                # deferred: merged into the next dot / norm that reads this vector (pmc_axpy_dot)
+                ctx.pending = (self, ind.start, float(alpha), x, xind.start)
+            else:
+                ctx.scalar[0] = alpha
+                ctx.call('pmc_axpy', self._ptr(ind.start), self.ld, x._ptr(xind.start), x.ld, 1, self.n,
+                         ctx.scalar_ptr, 1, 0)
+            return
+        self.space.ctx.flush()
         cols = _columns(ind, self._len)
         k = len(cols)
         a = _real_scalars(alpha, k)
@@ -359,6 +397,33 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return self.inner(self, ind, ind)
 
     def pairwise_inner(self, other, ind, oind, weight_ptr=0):
+        if (type(ind) is slice and type(oind) is slice and ind.step in (None, 1) and oind.step in (None, 1)
+                and ind.stop is not None and oind.stop is not None
+                and ind.stop - ind.start == 1 and oind.stop - oind.start == 1
+                and 0 <= ind.start < self._len and 0 <= oind.start < other._len):
+            # fast path: a single pair of vectors (Gram-Schmidt projection coefficient / norm)
+            sp = self.space
+            ctx = sp.ctx
+            pend = ctx.pending
+            if pend is not None:
+                timpl, tcol, alpha, ximpl, xcol = pend
+                same = other is self and ind.start == oind.start
+                if other is timpl and oind.start == tcol and (same or not (self is timpl and ind.start == tcol)):
+                    # the pending `v += alpha x` and this `<q, v>` (or ||v||^2) run as ONE pass over v
+                    ctx.pending = None
+                    out, flags = sp.reduction_target(1)
+                    ctx.scalar[0] = alpha
+                    ctx.call('pmc_axpy_dot', timpl._ptr(tcol), ximpl._ptr(xcol), ctx.scalar_ptr,
+                             0 if same else self._ptr(ind.start), self.n, weight_ptr, out.data_ptr(), flags)
+                    return sp.reduction_result(out, 1)
+                ctx.flush()
+            out, flags = sp.reduction_target(1)
+            if other is self and ind.start == oind.start:
+                sp.ctx.call('pmc_norm2', self._ptr(ind.start), self.ld, 1, self.n, weight_ptr, out.data_ptr(), flags)
+            else:
+                sp.ctx.call('pmc_pairwise_inner', self._ptr(ind.start), self.ld, other._ptr(oind.start), other.ld,
+                            1, self.n, weight_ptr, out.data_ptr(), flags)
+            return sp.reduction_result(out, 1)
         pa, csa, ka, keep_a = self._panel(ind)
         if ka == 0:
             return np.zeros(0)
@@ -468,6 +533,7 @@ class CudaVectorArray(VectorArray):
     def to_torch(self):
         """Zero-copy ``(len, local_dim)`` torch view of the (non-view) array's shard."""
         impl = self.impl
+        self.space.ctx.flush()
         prog = _progression(self.ind, impl._len)
         if prog is None or prog[1] < 1:
             impl, prog = impl._copied(self.ind), (0, 1, self._len)
@@ -561,6 +627,8 @@ class CudaVectorSpace(VectorSpace):
 
     # -- factory ------------------------------------------------------------------------------
     def __eq__(self, other):
+        if other is self:
+            return True
         return (type(other) is type(self) and self.dim == other.dim and self.id == other.id
                 and self.device == other.device and self._comm == other._comm)
 

@@ -128,6 +128,14 @@ class EmulatedLib:
             _col(Y, csY, c, n)[:] += al[c if n_alpha > 1 else 0] * x[:, c]
         return PMC_OK
 
+    def pmc_axpy_dot(self, ctx, Y, X, alpha, Q, n, w, out, flags):
+        self._note('pmc_axpy_dot')
+        y = _vec(Y, n)
+        y += _vec(alpha, 1)[0] * _vec(X, n).copy()
+        b = y * _vec(w, n) if w else y
+        _vec(out, 1)[0] = np.sum((_vec(Q, n) if Q else y) * b)
+        return PMC_OK
+
     def pmc_scal(self, ctx, Y, csY, k, n, alpha, n_alpha, flags):
         self._note('pmc_scal')
         al = _vec(alpha, n_alpha)

@@ -363,3 +363,29 @@ def test_shifted_chol_qr_golden(loaded_lib):
     D = Q.lincomb(R)
     D.axpy(-1.0, A)
     assert np.max(D.norm(prod) / A.norm(prod)) < 1e-13
+
+
+@pytest.mark.parametrize('dim', [5, 2048, 100003, 2000000])
+def test_fused_axpy_dot_bitwise_equals_separate_kernels(loaded_lib, rng, dim):
+    """The deferred axpy merged with the following dot/norm (pmc_axpy_dot) must give the very bits of
+    pmc_axpy + pmc_pairwise_inner / pmc_norm2 -- Gram-Schmidt results do not depend on the fusion."""
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaDiagonalOperator
+    sp = space_of(dim)
+    k = 6
+    A = rng.standard_normal((dim, k)) + 2 * rng.standard_normal((dim, 1))
+    w = rng.uniform(0.5, 1.5, dim)
+    prod = CudaDiagonalOperator(w, sp)
+    ctx = sp.ctx
+    results = []
+    for fuse in (True, False):
+        ctx.fuse_axpy = fuse
+        before = ctx.launch_count
+        Q, R = alg.gram_schmidt(sp.from_numpy(A), product=prod, return_R=True)
+        results.append((Q.to_numpy(), R, ctx.launch_count - before))
+    ctx.fuse_axpy = True
+    np.testing.assert_array_equal(results[0][0], results[1][0])
+    np.testing.assert_array_equal(results[0][1], results[1][1])
+    assert results[0][2] < results[1][2]                     # fewer launches with the fusion
+    Qo, Ro = O.gram_schmidt(A, w, return_R=True)
+    np.testing.assert_allclose(results[0][1], Ro, rtol=1e-11, atol=1e-11)

@@ -340,3 +340,62 @@ def test_standalone_shifted_chol_qr_golden(emu):
     # the default kernel applies the shift as well (the reference raises AttributeError there)
     Q = alg.shifted_chol_qr(sp.from_numpy(g['A_ill']))
     assert O.orthogonality_error(Q.to_numpy()) < 1e-12
+
+
+def test_deferred_axpy_fusion_semantics(emu, rng):
+    """`v.axpy(a, q)` on single vectors is deferred and merged with the next dot/norm on v
+    (pmc_axpy_dot); any other access must see the updated v, and q must be read before it changes."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    from pymor_b200.vectorarray import CudaVectorSpace
+    dim = 33
+    sp = space_of(dim)
+    A = rng.standard_normal((dim, 5))
+    w = rng.uniform(0.5, 1.5, dim)
+    prod = CudaDiagonalOperator(w, sp)
+
+    def fresh():
+        return sp.from_numpy(A)
+
+    # fused with the next dot (Gram-Schmidt order: q.pairwise_inner(v)) and with the norm
+    V = fresh(); emu.calls.clear()
+    V[2].axpy(-0.5, V[0])
+    p = V[1].pairwise_inner(V[2], prod)[0]
+    assert emu.calls == ['pmc_axpy_dot']
+    ref = A[:, 2] - 0.5 * A[:, 0]
+    np.testing.assert_allclose(p, np.sum(A[:, 1] * w * ref), rtol=1e-14)
+    V[2].axpy(0.25, V[1])
+    nrm = V[2].norm(prod)[0]
+    assert emu.calls == ['pmc_axpy_dot', 'pmc_axpy_dot']
+    ref = ref + 0.25 * A[:, 1]
+    np.testing.assert_allclose(nrm, np.sqrt(np.sum(ref * w * ref)), rtol=1e-14)
+    np.testing.assert_allclose(V.to_numpy()[:, 2], ref, atol=1e-15)
+    # not fusable orders fall back to axpy + reduction, same numbers
+    V = fresh(); emu.calls.clear()
+    V[2].axpy(-0.5, V[0])
+    p2 = V[2].pairwise_inner(V[1], prod)[0]                 # target is the FIRST operand
+    assert emu.calls == ['pmc_axpy', 'pmc_pairwise_inner']
+    np.testing.assert_allclose(p2, np.sum((A[:, 2] - 0.5 * A[:, 0]) * w * A[:, 1]), rtol=1e-14)
+    # the source vector is modified right after: the deferred axpy must have used the OLD source
+    V = fresh()
+    V[2].axpy(2.0, V[0])
+    V[0].scal(100.0)
+    np.testing.assert_allclose(V.to_numpy()[:, 2], A[:, 2] + 2.0 * A[:, 0], atol=1e-14)
+    # ... also when the source lives in another array of an equal-but-distinct space object
+    sp2 = CudaVectorSpace(dim, device='cpu')
+    assert sp2 == sp and sp2 is not sp
+    Q = sp2.from_numpy(A[:, [0]])
+    V = fresh()
+    V[3].axpy(-1.5, Q[0])
+    Q.scal(0.0)
+    np.testing.assert_allclose(V.to_numpy()[:, 3], A[:, 3] - 1.5 * A[:, 0], atol=1e-14)
+    # every other consumer sees the update: copy, lincomb, inner, gramian, dofs, append, two deferrals in a row
+    V = fresh(); V[1].axpy(1.0, V[4]); C = V.copy(deep=True)
+    np.testing.assert_allclose(C.to_numpy()[:, 1], A[:, 1] + A[:, 4], atol=1e-15)
+    V = fresh(); V[1].axpy(1.0, V[4])
+    np.testing.assert_allclose(V.lincomb(np.eye(5)[:, [1]]).to_numpy()[:, 0], A[:, 1] + A[:, 4], atol=1e-15)
+    V = fresh(); V[1].axpy(1.0, V[4]); V[2].axpy(-1.0, V[1])
+    ref = A.copy(); ref[:, 1] += ref[:, 4]; ref[:, 2] -= ref[:, 1]
+    np.testing.assert_allclose(V.gramian(prod), O.gramian(ref, w), atol=1e-13)
+    np.testing.assert_allclose(V.dofs([0, 7]), O.dofs(ref, [0, 7]), atol=1e-15)
+    V = fresh(); V[0].axpy(3.0, V[1]); W2 = sp.empty(); W2.append(V[0])
+    np.testing.assert_allclose(W2.to_numpy()[:, 0], A[:, 0] + 3.0 * A[:, 1], atol=1e-15)
