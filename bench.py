@@ -40,6 +40,13 @@ sys.path.insert(0, str(ROOT))
 METRIC = 'POD (method_of_snapshots, diag-W product) FP64 TFLOP/s, 10M DOF x 1000 snapshots per GPU'
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE lincomb_dmma_kernel launch, from an `ncu --set full`
+# capture of this very workload (n per GPU, k, m); equals the algorithmic 8*n*(k+m) = 160.0 GB to 0.1 %.
+NCU_TRAFFIC = {(10_000_000, 1000, 1000): 80.138563e9 + 79.989229e9,
+               (2_000_000, 500, 500): 8.006061e9 + 7.963813e9}
+NCU_TRAFFIC_SOURCE = 'profiles/r01_ncu_full_lincomb_10Mx1000_details.txt, profiles/r01b_ncu_full_details.txt'
+
+
 def pod_flops(n, k, m):
     """Algorithmic flop of POD by the method of snapshots: SYRK Gramian + lincomb +
     orthonormality-check Gramian."""
@@ -282,7 +289,10 @@ def run_cuda(args):
     gram_ms = float(np.mean(phases['gramian'])) if phases['gramian'] else float('nan')
     gram_tf = n_local * k * (k + 1) / (gram_ms * 1e-3) * 1e-12   # both Gramians here are k x k SYRK (m == k) or m x m
     roofline = {'bound': 'tensor', 'kernel': 'lincomb_dmma_kernel', 'achieved': achieved, 'peak': peak_dmma,
-                'unit': 'TFLOP/s', 'frac': achieved / peak_dmma if peak_dmma else None, 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': achieved / peak_dmma if peak_dmma else None,
+                'traffic': NCU_TRAFFIC.get((n_local, k, int(m))),
+                'traffic_source': NCU_TRAFFIC_SOURCE if (n_local, k, int(m)) in NCU_TRAFFIC else None,
+                'algorithmic_bytes_per_launch': 8.0 * n_local * (k + m),
                 'peak_source': 'FP64 tensor-core (DMMA.8x8x4) issue-rate microbenchmark measured in this run '
                                '(pmc_measure_fp64_peak); MEASURED_PEAKS.json carries no fp64 figure',
                 'dfma_peak_tflops': peak_dfma,

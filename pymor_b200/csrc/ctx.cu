@@ -64,7 +64,7 @@ extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
     const char *go = getenv("PMC_GRAM_OPTS");
     c->gram_opts = go ? atoi(go) : 0;
     const char *gw = getenv("PMC_GRAM_WAVES");
-    c->gram_waves = (gw && atoi(gw) > 0) ? atoi(gw) : 16;
+    c->gram_waves = (gw && atoi(gw) > 0) ? atoi(gw) : 32;
     *out = c;
     return PMC_OK;
 }
