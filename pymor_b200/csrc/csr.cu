@@ -49,6 +49,64 @@ csr_apply_kernel(int64_t row0, int64_t nrows, const int64_t *__restrict__ rowptr
         if (j0 + jj < k) Y[r + (int64_t)(j0 + jj) * csY] = acc[jj];
 }
 
+// Row-tile variant: the block's slice of (colidx, vals) is staged in shared memory with coalesced
+// loads, so the gathers of X are not queued behind dependent matrix loads; every thread owns one row
+// and walks CT_COLS panel columns four at a time (four independent gathers per matrix entry).
+constexpr int CT_ROWS = 128, CT_COLS = 32, CT_MAXNZ = CT_ROWS * 24;
+
+__global__ void __launch_bounds__(CT_ROWS)
+csr_apply_tiled_kernel(int64_t row0, int64_t nrows, const int64_t *__restrict__ rowptr,
+                       const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+                       const double *__restrict__ X, int64_t csX, int64_t n_local,
+                       const double *__restrict__ ghost, double *__restrict__ Y, int64_t csY, int k) {
+    __shared__ int32_t s_col[CT_MAXNZ];
+    __shared__ double s_val[CT_MAXNZ];
+    const int64_t rb = (int64_t)blockIdx.x * CT_ROWS;
+    const int rows = (int)((nrows - rb < CT_ROWS) ? nrows - rb : CT_ROWS);
+    const int64_t pb = rowptr[row0 + rb], pe = rowptr[row0 + rb + rows];
+    const int cnt = (int)(pe - pb);
+    const bool staged = cnt <= CT_MAXNZ;
+    if (staged) {
+        for (int i = threadIdx.x; i < cnt; i += CT_ROWS) {
+            s_col[i] = colidx[pb + i];
+            s_val[i] = vals[pb + i];
+        }
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= rows) return;
+    const int64_t r = rb + t;
+    const int64_t p0 = rowptr[row0 + r], p1 = rowptr[row0 + r + 1];
+    const int j_begin = blockIdx.y * CT_COLS;
+    const int j_end = (j_begin + CT_COLS < k) ? j_begin + CT_COLS : k;
+    for (int j = j_begin; j < j_end; j += 4) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const int nj = j_end - j;
+        for (int64_t p = p0; p < p1; ++p) {
+            const double v = staged ? s_val[p - pb] : vals[p];
+            const int64_t col = staged ? s_col[p - pb] : colidx[p];
+            if (col < n_local) {
+                const double *x = X + col + (int64_t)j * csX;
+                a0 = fma(v, x[0], a0);
+                if (nj > 1) a1 = fma(v, x[csX], a1);
+                if (nj > 2) a2 = fma(v, x[2 * csX], a2);
+                if (nj > 3) a3 = fma(v, x[3 * csX], a3);
+            } else {
+                const double *gx = ghost + (col - n_local) * k + j;
+                a0 = fma(v, gx[0], a0);
+                if (nj > 1) a1 = fma(v, gx[1], a1);
+                if (nj > 2) a2 = fma(v, gx[2], a2);
+                if (nj > 3) a3 = fma(v, gx[3], a3);
+            }
+        }
+        double *y = Y + r + (int64_t)j * csY;
+        y[0] = a0;
+        if (nj > 1) y[csY] = a1;
+        if (nj > 2) y[2 * csY] = a2;
+        if (nj > 3) y[3 * csY] = a3;
+    }
+}
+
 // halo packing: out[r * k + j] = A[idx[r] + j * csA]   (idx on the device)
 __global__ void gather_rows_kernel(const double *__restrict__ A, int64_t csA, int k,
                                    const int64_t *__restrict__ idx, int64_t nidx, double *__restrict__ out) {
@@ -62,9 +120,15 @@ __global__ void gather_rows_kernel(const double *__restrict__ A, int64_t csA, in
 int launch_csr_apply(pmc_ctx *ctx, int64_t row0, int64_t nrows, const int64_t *rowptr,
                      const int32_t *colidx, const double *vals, const double *X, int64_t csX,
                      int64_t n_local, const double *ghost, double *Y, int64_t csY, int k) {
-    dim3 grid((unsigned)ceil_div64(nrows, CSR_THREADS), (k + CJ - 1) / CJ);
-    csr_apply_kernel<<<grid, CSR_THREADS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX,
-                                                          n_local, ghost, Y, csY, k);
+    if (ctx->csr_variant == 0) {
+        dim3 grid((unsigned)ceil_div64(nrows, CT_ROWS), (k + CT_COLS - 1) / CT_COLS);
+        csr_apply_tiled_kernel<<<grid, CT_ROWS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX,
+                                                                  n_local, ghost, Y, csY, k);
+    } else {
+        dim3 grid((unsigned)ceil_div64(nrows, CSR_THREADS), (k + CJ - 1) / CJ);
+        csr_apply_kernel<<<grid, CSR_THREADS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX,
+                                                              n_local, ghost, Y, csY, k);
+    }
     ctx->launches += 1;
     PMC_CHECK_CUDA(cudaGetLastError());
     return PMC_OK;

@@ -63,6 +63,8 @@ extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
     c->l2_keep = (nk && nk[0] == '1') ? 0 : 1;
     const char *go = getenv("PMC_GRAM_OPTS");
     c->gram_opts = go ? atoi(go) : 0;
+    const char *cv = getenv("PMC_CSR_VARIANT");
+    c->csr_variant = cv ? atoi(cv) : 0;
     const char *gw = getenv("PMC_GRAM_WAVES");
     c->gram_waves = (gw && atoi(gw) > 0) ? atoi(gw) : 32;
     *out = c;
