@@ -120,7 +120,7 @@ __global__ void gather_rows_kernel(const double *__restrict__ A, int64_t csA, in
 int launch_csr_apply(pmc_ctx *ctx, int64_t row0, int64_t nrows, const int64_t *rowptr,
                      const int32_t *colidx, const double *vals, const double *X, int64_t csX,
                      int64_t n_local, const double *ghost, double *Y, int64_t csY, int k) {
-    if (ctx->csr_variant == 0) {
+    if (ctx->csr_variant == 1) {
         dim3 grid((unsigned)ceil_div64(nrows, CT_ROWS), (k + CT_COLS - 1) / CT_COLS);
         csr_apply_tiled_kernel<<<grid, CT_ROWS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX,
                                                                   n_local, ghost, Y, csY, k);
@@ -161,8 +161,11 @@ extern "C" int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, 
     PMC_REQUIRE(rowptr && colidx && vals && V && U, "NULL pointer");
 
     // Workspace layout: [ T panel (PR x kU, leading dimension PR) | Gram split partials ].
-    // The T panel is kept <= 48 MB so that it is still in the 126 MB L2 when the Gram kernel reads it.
-    const size_t panel_budget = (size_t)48 << 20;
+    // The panel is sized for the Gram kernel, not for L2: with >= ~30k rows per panel the split-n
+    // decomposition has enough items to fill the SMs evenly (a 3k-row panel at k = 2000 gave 256 items
+    // on 148 SMs, i.e. two ragged waves), while writing the panel to HBM and reading it back costs
+    // 16*n*k bytes in total -- 2 % of the contraction time at k = 2000.
+    const size_t panel_budget = (size_t)512 << 20;
     int64_t PR = (int64_t)(panel_budget / ((size_t)kU * 8));
     PR = (PR / 128) * 128;
     if (PR < 2048) PR = 2048;

@@ -63,8 +63,12 @@ def main():
     torch.cuda.synchronize()
 
     def timed(fn):
+        t_end = time.perf_counter() + 0.3                 # warm-up at least 0.3 s: short runs start from idle clocks
         fn()
         torch.cuda.synchronize()
+        while time.perf_counter() < t_end:
+            fn()
+            torch.cuda.synchronize()
         if comm:
             comm.barrier()
         t0 = time.perf_counter()
