@@ -57,6 +57,8 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
                 q = A[j]
                 p = q.pairwise_inner(v, product)[0]
                 v.axpy(-p, q)
+                if np.iscomplexobj(p) and not np.iscomplexobj(R):
+                    R = R.astype(np.complex128)
                 R[j, i] += p
             prev, cur = cur, v.norm(product)[0]
             if cur <= rtol * norm0:

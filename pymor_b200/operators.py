@@ -18,13 +18,20 @@ import numpy as np
 import scipy.sparse as sps
 import torch
 
-from pymor_b200._lib import PMC_SYNC
+from pymor_b200.complexarray import CudaComplexVectorArrayImpl
 from pymor_b200.interface import Operator
-from pymor_b200.vectorarray import CudaVectorArray, CudaVectorArrayImpl, CudaVectorSpace, _same_index
+from pymor_b200.vectorarray import CudaVectorArray, CudaVectorArrayImpl, CudaVectorSpace
 
 
-def _same_columns(V, U):
-    return V.impl is U.impl and _same_index(V.ind, U.ind)
+def _is_complex(U):
+    return type(U.impl) is CudaComplexVectorArrayImpl
+
+
+def _apply_by_parts(op, U):
+    """A real linear operator acts on the real and imaginary parts separately."""
+    fn = op.apply if hasattr(op, 'apply') else op
+    re, im = fn(U.real), fn(U.imag)
+    return CudaVectorArray(U.space, CudaComplexVectorArrayImpl(U.space, re.impl, im.impl))
 
 
 class CudaDiagonalOperator(Operator):
@@ -68,6 +75,8 @@ class CudaDiagonalOperator(Operator):
 
     def apply(self, U, mu=None):
         assert U in self.source
+        if _is_complex(U):
+            return _apply_by_parts(self, U)
         pu, csu, k, keep = U.impl._panel(U.ind)
         out = CudaVectorArrayImpl.allocate(self.space, k)
         if k and self.space.local_dim:
@@ -198,6 +207,8 @@ class CudaCsrOperator(Operator):
         return op
 
     def _apply_csr(self, blk, U):
+        if _is_complex(U):
+            return _apply_by_parts(lambda W: self._apply_csr(blk, W), U)
         pu, csu, k, keep = U.impl._panel(U.ind)
         out = CudaVectorArrayImpl.allocate(self.space, k)
         n = self.space.local_dim
@@ -223,6 +234,8 @@ class CudaCsrOperator(Operator):
 
     def apply2(self, V, U, mu=None):
         assert V in self.range and U in self.source
+        if _is_complex(V) or _is_complex(U):
+            return V.inner(self.apply(U))
         pv, csv, kv, keep_v = V.impl._panel(V.ind)
         pu, csu, ku, keep_u = U.impl._panel(U.ind)
         if kv == 0 or ku == 0:

@@ -11,8 +11,9 @@ kernels) through the C ABI of include/pymor_b200.h.  There is no CPU fallback.
 With a communicator the rows are sharded over ranks (one process per GPU) exactly like
 ``MPIVectorArrayAutoComm`` (src/pymor/vectorarrays/mpi.py:316-445).
 
-Complex numbers: the north star is fp64; complex input raises ``NotImplementedError`` (pyMOR's own
-contract tests tolerate this for backends, src/pymortests/vectorarray.py:66-69).
+Complex numbers: the performance path is real fp64.  Complex arrays (pyMOR's contract includes them and
+in-place promotion such as ``v.scal(1j)``) are a pair of real arrays, every operation composed from the
+real kernels -- see pymor_b200/complexarray.py.
 """
 from __future__ import annotations
 
@@ -118,6 +119,12 @@ def _consecutive_runs(cols):
     return out
 
 
+def _is_complex_value(alpha):
+    """True for a Python/NumPy complex scalar or complex ndarray (whatever its imaginary part): the
+    reference promotes on the coefficient's dtype, not on its value (numpy.py:90-95)."""
+    return isinstance(alpha, (complex, np.complexfloating)) or (type(alpha) is np.ndarray and np.iscomplexobj(alpha))
+
+
 def _real_scalars(alpha, count):
     """alpha (Number | ndarray (count,)) -> contiguous float64 host array of 1 or ``count`` values."""
     a = np.asarray(alpha)
@@ -145,6 +152,19 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         alloc = torch.zeros if zero else torch.empty
         buf = alloc((cap, space.ld), dtype=torch.float64, device=space.device)
         return cls(space, buf, count)
+
+    def _promote(self):
+        """In-place promotion to complex (the reference does `self._array = self._array.astype(...)`,
+        numpy.py:90-95): this object becomes a CudaComplexVectorArrayImpl whose real part adopts the
+        buffer; views and copy-on-write references keep pointing at the same impl object."""
+        from pymor_b200.complexarray import CudaComplexVectorArrayImpl
+        self.space.ctx.flush()
+        re = CudaVectorArrayImpl(self.space, self._buf_t, self._len)
+        for name in ('_buf_t', '_base', '_ld', '_len'):
+            del self.__dict__[name]
+        self.__class__ = CudaComplexVectorArrayImpl
+        self._re, self._im = re, None
+        return self
 
     # the buffer's address and leading dimension are cached: they are read on every kernel call
     @property
@@ -258,6 +278,8 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         self._len = len(keep)
 
     def append(self, other, remove_from_other, oind):
+        if type(other) is not CudaVectorArrayImpl:            # complex data arrives: promote in place
+            return self._promote().append(other, remove_from_other, oind)
         self.space.ctx.flush()
         k_other = other.len_ind(oind)
         if k_other == 0:
@@ -291,6 +313,8 @@ class CudaVectorArrayImpl(VectorArrayImpl):
             other.delete(oind)
 
     def scal(self, alpha, ind):
+        if _is_complex_value(alpha):
+            return self._promote().scal(alpha, ind)
         self.space.ctx.flush()
         cols = _columns(ind, self._len)
         if len(cols) == 0 or self.n == 0:
@@ -314,6 +338,8 @@ class CudaVectorArrayImpl(VectorArrayImpl):
     def axpy(self, alpha, x, ind, xind):
         # fast path of the Gram-Schmidt inner step: one vector += scalar * another vector, both
         # addressed by the unit slices ``A[i]`` / ``A[j]`` produce (interface.py:219-223)
+        if type(x) is not CudaVectorArrayImpl or _is_complex_value(alpha):
+            return self._promote().axpy(alpha, x, ind, xind)
         if (type(ind) is slice and type(xind) is slice and type(alpha) in _FLOAT_TYPES
                 and ind.step in (None, 1) and xind.step in (None, 1)
                 and ind.stop is not None and xind.stop is not None
@@ -356,6 +382,9 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         del keep
 
     def inner(self, other, ind, oind, weight_ptr=0):
+        if type(other) is not CudaVectorArrayImpl:
+            from pymor_b200.complexarray import CudaComplexVectorArrayImpl
+            return CudaComplexVectorArrayImpl.wrap(self).inner(other, ind, oind, weight_ptr=weight_ptr)
         pa, csa, ka, keep_a = self._panel(ind)
         symmetric = other is self and _same_index(ind, oind)
         if symmetric:
@@ -397,6 +426,9 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         return self.inner(self, ind, ind)
 
     def pairwise_inner(self, other, ind, oind, weight_ptr=0):
+        if type(other) is not CudaVectorArrayImpl:
+            from pymor_b200.complexarray import CudaComplexVectorArrayImpl
+            return CudaComplexVectorArrayImpl.wrap(self).pairwise_inner(other, ind, oind, weight_ptr=weight_ptr)
         if (type(ind) is slice and type(oind) is slice and ind.step in (None, 1) and oind.step in (None, 1)
                 and ind.stop is not None and oind.stop is not None
                 and ind.stop - ind.start == 1 and oind.stop - oind.start == 1
@@ -456,9 +488,9 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         pa, csa, k, keep = self._panel(ind)
         coefficients = np.asarray(coefficients)
         if np.iscomplexobj(coefficients):
-            if np.any(coefficients.imag != 0):
-                raise NotImplementedError('complex lincomb coefficients are not supported')
-            coefficients = coefficients.real
+            from pymor_b200.complexarray import CudaComplexVectorArrayImpl
+            del keep
+            return CudaComplexVectorArrayImpl.wrap(self).lincomb(coefficients, ind)
         assert coefficients.ndim == 2 and coefficients.shape[0] == k
         m = coefficients.shape[1]
         new = CudaVectorArrayImpl.allocate(self.space, m)
@@ -525,14 +557,19 @@ def _same_index(a, b):
     return a == b
 
 
+from pymor_b200.complexarray import CudaComplexVectorArrayImpl  # noqa: E402
+
+
 class CudaVectorArray(VectorArray):
     """|VectorArray| whose vectors live in B200 HBM."""
 
-    impl_type = CudaVectorArrayImpl
+    impl_type = (CudaVectorArrayImpl, CudaComplexVectorArrayImpl)
 
     def to_torch(self):
         """Zero-copy ``(len, local_dim)`` torch view of the (non-view) array's shard."""
         impl = self.impl
+        if type(impl) is not CudaVectorArrayImpl:
+            raise NotImplementedError('DLPack / torch export is defined for real arrays only')
         self.space.ctx.flush()
         prog = _progression(self.ind, impl._len)
         if prog is None or prog[1] < 1:
@@ -642,7 +679,8 @@ class CudaVectorSpace(VectorSpace):
     def full(self, value, count=1, reserve=0):
         assert count >= 0 and reserve >= 0
         if isinstance(value, complex) or np.iscomplexobj(value):
-            raise NotImplementedError('complex values are not supported')
+            re, im = self.full(complex(value).real, count, reserve), self.full(complex(value).imag, count, reserve)
+            return CudaVectorArray(self, CudaComplexVectorArrayImpl(self, re.impl, im.impl))
         impl = CudaVectorArrayImpl.allocate(self, count, reserve)
         impl._buf[:count].fill_(float(value))
         return CudaVectorArray(self, impl)
@@ -669,7 +707,8 @@ class CudaVectorSpace(VectorSpace):
     def _upload(self, data, reserve=0):
         data = np.asarray(data)
         if np.iscomplexobj(data):
-            raise NotImplementedError('CudaVectorArray is real fp64; complex data is not supported')
+            re, im = self._upload(data.real, reserve), self._upload(data.imag, reserve)
+            return CudaVectorArray(self, CudaComplexVectorArrayImpl(self, re.impl, im.impl))
         if data.ndim == 1:
             data = data.reshape((-1, 1))
         assert data.ndim == 2 and data.shape[0] == self.dim
@@ -685,7 +724,8 @@ class CudaVectorSpace(VectorSpace):
         shard (one vector per contiguous column) in pinned memory is copied by a single DMA."""
         shard = np.asarray(shard)
         if np.iscomplexobj(shard):
-            raise NotImplementedError('CudaVectorArray is real fp64; complex data is not supported')
+            re, im = self.from_local_numpy(shard.real, reserve), self.from_local_numpy(shard.imag, reserve)
+            return CudaVectorArray(self, CudaComplexVectorArrayImpl(self, re.impl, im.impl))
         assert shard.ndim == 2 and shard.shape[0] == self._local_dim
         count = shard.shape[1]
         impl = CudaVectorArrayImpl.allocate(self, count, reserve)

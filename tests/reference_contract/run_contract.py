@@ -3,8 +3,8 @@
 Build-container only (needs /root/reference).  The reference parametrises its VectorArray tests over
 backend names looked up in ``pymortests.strategies`` (src/pymortests/strategies.py:110-184); external
 backends register by adding a ``_<name>_vector_spaces`` factory.  We register ``'cuda'`` from here
-(the reference tree is read-only and stays untouched), restrict the drawn dtype to float64 (the
-backend is real fp64 by design) and hand over to pytest.
+(the reference tree is read-only and stays untouched) and hand over to pytest; hypothesis draws
+float64 and complex128 inputs exactly as for the reference's own backends.
 
 Without a GPU the C ABI is served by tests/emulated_lib.py (NumPy), so what this validates is the
 host-side view / copy-on-write / aliasing / growth logic and the pyMOR integration; with a GPU
@@ -55,7 +55,6 @@ def _cuda_vector_spaces(draw, np_data_list, compatible, count, dims):
 pyst._cuda_vector_spaces = _cuda_vector_spaces
 pyst._picklable_vector_space_types = []
 pyst._other_vector_space_types = ['cuda']
-pyst.hy_dtypes = hyst.just(np.float64)
 
 import pytest  # noqa: E402
 

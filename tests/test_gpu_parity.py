@@ -389,3 +389,31 @@ def test_fused_axpy_dot_bitwise_equals_separate_kernels(loaded_lib, rng, dim):
     assert results[0][2] < results[1][2]                     # fewer launches with the fusion
     Qo, Ro = O.gram_schmidt(A, w, return_R=True)
     np.testing.assert_allclose(results[0][1], Ro, rtol=1e-11, atol=1e-11)
+
+
+def test_complex_arrays_on_device(loaded_lib, rng):
+    """Complex arrays (pairs of real device arrays, pymor_b200/complexarray.py) against NumPy."""
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaDiagonalOperator
+    dim, k = 4099, 20
+    sp = space_of(dim)
+    A = rng.standard_normal((dim, k)) + 1j * rng.standard_normal((dim, k))
+    B = rng.standard_normal((dim, k)) + 1j * rng.standard_normal((dim, k))
+    w = rng.uniform(0.5, 1.5, dim)
+    VA, VB, prod = sp.from_numpy(A), sp.from_numpy(B), CudaDiagonalOperator(w, sp)
+    scale = np.outer(np.linalg.norm(A, axis=0), np.linalg.norm(B, axis=0))
+    assert np.max(np.abs(VA.inner(VB) - A.conj().T @ B) / scale) < 1e-12
+    assert np.max(np.abs(VA.inner(VB, prod) - A.conj().T @ (w[:, None] * B)) / scale) < 1e-12
+    np.testing.assert_allclose(VA.pairwise_inner(VB), np.sum(A.conj() * B, axis=0), atol=1e-10)
+    np.testing.assert_allclose(VA.norm(), np.linalg.norm(A, axis=0), rtol=1e-13)
+    C = rng.standard_normal((k, 17)) + 1j * rng.standard_normal((k, 17))
+    np.testing.assert_allclose(VA.lincomb(C).to_numpy(), A @ C, atol=1e-11)
+    Y = sp.from_numpy(A.real); Y.scal(1j)                       # in-place promotion
+    np.testing.assert_allclose(Y.to_numpy(), 1j * A.real, atol=1e-15)
+    Y = VA.copy(); Y.axpy(0.5 - 2j, VB)
+    np.testing.assert_allclose(Y.to_numpy(), A + (0.5 - 2j) * B, atol=1e-13)
+    idx, val = VA.amax()
+    np.testing.assert_array_equal(idx, np.argmax(np.abs(A), axis=0))
+    Q, R = alg.gram_schmidt(VA, product=prod, return_R=True)
+    np.testing.assert_allclose(Q.lincomb(R).to_numpy(), A, atol=1e-11)
+    np.testing.assert_allclose(Q.gramian(prod), np.eye(k), atol=1e-12)
