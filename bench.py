@@ -321,10 +321,13 @@ def run_cuda(args):
         last = {}
 
         def e2e_step():
-            arr = space.empty(reserve=k)
-            for c0 in range(0, k, k_host):                # public API: host chunk -> HBM, appended
-                kc = min(k_host, k - c0)
-                arr.append(space.from_local_numpy(host_np[:, :kc]), remove_from_other=True)
+            if k_host == k:                               # public API: host shard -> HBM (copy stream; the
+                arr = space.from_local_numpy(host_np)     # Gramian starts on the column blocks as they land)
+            else:
+                arr = space.empty(reserve=k)
+                for c0 in range(0, k, k_host):            # host chunk -> HBM, appended
+                    kc = min(k_host, k - c0)
+                    arr.append(space.from_local_numpy(host_np[:, :kc]), remove_from_other=True)
             U, s = pod_step(arr)
             last['s'] = np.array(s)                       # singular values arrive on the host
             mm = len(U)

@@ -119,6 +119,8 @@ class DeviceContext:
         self.ensure_workspace(64 << 20)
         # deferred single-vector axpy (see CudaVectorArrayImpl.axpy): at most one per device, flushed by
         # any other operation; merged with the next dot/norm on its target by pmc_axpy_dot
+        self.uploads = []                              # impls whose host -> device copy is still in flight
+        self._copy_stream = None
         self.pending = None
         self.fuse_axpy = os.environ.get('PMC_NO_FUSE_AXPY', '0') != '1'
         self.scalar = np.zeros(1)                      # staging for scalar coefficients (read at launch)
@@ -151,8 +153,26 @@ class DeviceContext:
         if rc != PMC_OK:
             raise PmcError(f'{name} failed ({rc}): {self._err()}')
 
+    def copy_stream(self):
+        """Side stream for host -> device uploads that overlap with compute."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
+
+    def wait_uploads(self):
+        """Make the compute stream wait for every upload still in flight."""
+        ups, self.uploads = self.uploads, []
+        cur = torch.cuda.current_stream(self.device)
+        for impl in ups:
+            for _, _, ev in impl._arrivals or ():
+                cur.wait_event(ev)
+            impl._arrivals = None
+            impl._arrival_src = None
+
     def flush(self):
-        """Launch the deferred axpy, if any."""
+        """Launch the deferred axpy, if any; order the stream after uploads still in flight."""
+        if self.uploads:
+            self.wait_uploads()
         pend = self.pending
         if pend is not None:
             self.pending = None

@@ -31,6 +31,8 @@ from pymor_b200.interface import HAVE_PYMOR, VectorArray, VectorArrayImpl, Vecto
 _ALIGN = 16  # doubles
 _FLOAT_TYPES = (float, np.float64, int)
 _HOST_REDUCE_MAX = 2048  # sharded reductions of at most this many doubles are summed on the host
+_STREAMED_UPLOAD_BYTES = 256 << 20   # pinned shards at least this large are uploaded on a side stream
+_UPLOAD_BLOCKS = 8                   # ... in this many column blocks
 _SKINNY = 4  # inner products with at most this many vectors on one side use the streaming kernel
 
 
@@ -144,6 +146,8 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         self.space = space
         self._buf = buf
         self._len = int(length)
+        self._arrivals = None        # [(col_begin, col_end, event)] of a host -> device upload in flight
+        self._arrival_src = None
 
     # -- storage helpers -------------------------------------------------------------------
     @classmethod
@@ -160,8 +164,8 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         from pymor_b200.complexarray import CudaComplexVectorArrayImpl
         self.space.ctx.flush()
         re = CudaVectorArrayImpl(self.space, self._buf_t, self._len)
-        for name in ('_buf_t', '_base', '_ld', '_len'):
-            del self.__dict__[name]
+        for name in ('_buf_t', '_base', '_ld', '_len', '_arrivals', '_arrival_src'):
+            self.__dict__.pop(name, None)
         self.__class__ = CudaComplexVectorArrayImpl
         self._re, self._im = re, None
         return self
@@ -347,7 +351,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
                 and 0 <= ind.start < self._len and 0 <= xind.start < x._len and self.n
                 and not (x._buf is self._buf and ind.start == xind.start)):
             ctx = self.space.ctx
-            ctx.flush()
+            ctx.flush()                     # also orders the stream after uploads in flight
             if ctx.fuse_axpy:
                 # deferred: merged into the next dot / norm that reads this vector (pmc_axpy_dot)
                 ctx.pending = (self, ind.start, float(alpha), x, xind.start)
@@ -385,6 +389,9 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         if type(other) is not CudaVectorArrayImpl:
             from pymor_b200.complexarray import CudaComplexVectorArrayImpl
             return CudaComplexVectorArrayImpl.wrap(self).inner(other, ind, oind, weight_ptr=weight_ptr)
+        if (self._arrivals is not None and other is self and _same_index(ind, oind)
+                and _progression(ind, self._len) == (0, 1, self._len) and not self.space.kernel_flags):
+            return self._gramian_while_uploading(weight_ptr)
         pa, csa, ka, keep_a = self._panel(ind)
         symmetric = other is self and _same_index(ind, oind)
         if symmetric:
@@ -425,6 +432,35 @@ class CudaVectorArrayImpl(VectorArrayImpl):
     def gramian(self, ind):
         return self.inner(self, ind, ind)
 
+    def _gramian_while_uploading(self, weight_ptr):
+        """Gramian of an array whose host -> device upload is still in flight (from_local_numpy of
+        pinned data): column block b is contracted with blocks 0..b as soon as it has landed, so the
+        tensor-core work hides behind the PCIe transfer of the following blocks.  Only the upper block
+        triangle is computed (same flop as SYRK) and mirrored on the host."""
+        sp, ctx = self.space, self.space.ctx
+        arrivals, self._arrivals = self._arrivals, None
+        if self in ctx.uploads:
+            ctx.uploads.remove(self)
+        ctx.flush()
+        k = self._len
+        out, flags = sp.reduction_target(k * k)
+        cur = torch.cuda.current_stream(sp.device)
+        for c0, c1, ev in arrivals:
+            cur.wait_event(ev)
+            base = out.data_ptr() + 8 * c0 * k
+            ctx.call('pmc_gram', self._ptr(c0), self.ld, c1 - c0, self._ptr(c0), self.ld, c1 - c0, self.n,
+                     weight_ptr, base + 8 * c0, k, PMC_SYMMETRIC)
+            if c0:
+                ctx.call('pmc_gram', self._ptr(0), self.ld, c0, self._ptr(c0), self.ld, c1 - c0, self.n,
+                         weight_ptr, base, k, 0)
+        self._arrival_src = None
+        if flags & PMC_SYNC:
+            ctx.sync()
+        # the strictly lower blocks were never written: only the upper triangle of the scratch is used
+        raw = sp.reduction_result(out, k * k).reshape((k, k), order='F')
+        res = np.triu(raw)
+        return res + np.triu(raw, 1).T
+
     def pairwise_inner(self, other, ind, oind, weight_ptr=0):
         if type(other) is not CudaVectorArrayImpl:
             from pymor_b200.complexarray import CudaComplexVectorArrayImpl
@@ -436,6 +472,8 @@ class CudaVectorArrayImpl(VectorArrayImpl):
             # fast path: a single pair of vectors (Gram-Schmidt projection coefficient / norm)
             sp = self.space
             ctx = sp.ctx
+            if ctx.uploads:
+                ctx.wait_uploads()
             pend = ctx.pending
             if pend is not None:
                 timpl, tcol, alpha, ximpl, xcol = pend
@@ -732,7 +770,28 @@ class CudaVectorSpace(VectorSpace):
         if count and self._local_dim:
             rows = shard.T if shard.T.flags.c_contiguous and shard.dtype == np.float64 \
                 else np.ascontiguousarray(shard.T, dtype=np.float64)
-            impl._buf[:count, :self._local_dim].copy_(torch.from_numpy(rows), non_blocking=True)
+            src = torch.from_numpy(rows)
+            n = self._local_dim
+            if (self.device.type == 'cuda' and count >= 64 and src.numel() * 8 >= _STREAMED_UPLOAD_BYTES
+                    and src.is_pinned()):
+                # large pinned shard: copy column blocks on a side stream; consumers wait per block
+                # (the Gramian works on the blocks as they land, see _gramian_while_uploading)
+                blk = _round_up(-(-count // _UPLOAD_BLOCKS), 8)
+                cs = self._ctx.copy_stream()
+                cs.wait_stream(torch.cuda.current_stream(self.device))
+                arrivals = []
+                with torch.cuda.stream(cs):
+                    for c0 in range(0, count, blk):
+                        c1 = min(count, c0 + blk)
+                        impl._buf[c0:c1, :n].copy_(src[c0:c1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                        arrivals.append((c0, c1, ev))
+                impl._buf.record_stream(cs)
+                impl._arrivals, impl._arrival_src = arrivals, src
+                self._ctx.uploads.append(impl)
+            else:
+                impl._buf[:count, :n].copy_(src, non_blocking=True)
         return CudaVectorArray(self, impl)
 
     def from_numpy(self, data, ensure_copy=False):

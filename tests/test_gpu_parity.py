@@ -417,3 +417,37 @@ def test_complex_arrays_on_device(loaded_lib, rng):
     Q, R = alg.gram_schmidt(VA, product=prod, return_R=True)
     np.testing.assert_allclose(Q.lincomb(R).to_numpy(), A, atol=1e-11)
     np.testing.assert_allclose(Q.gramian(prod), np.eye(k), atol=1e-12)
+
+
+def test_gramian_while_uploading(loaded_lib, rng, monkeypatch):
+    """from_local_numpy of a pinned shard uploads on a side stream; the Gramian contracts the column
+    blocks as they land.  Same result as the resident path, symmetric, and every other consumer
+    (norm, lincomb, axpy fast path) sees complete data."""
+    import torch
+    from pymor_b200 import vectorarray as va
+    from pymor_b200.operators import CudaDiagonalOperator
+    monkeypatch.setattr(va, '_STREAMED_UPLOAD_BYTES', 1 << 16)
+    n, k = 30011, 200
+    sp = space_of(n)
+    host = torch.empty((k, n), dtype=torch.float64, pin_memory=True)
+    host.copy_(torch.from_numpy(rng.standard_normal((k, n))))
+    A = host.numpy().T
+    w = rng.uniform(0.5, 1.5, n)
+    prod = CudaDiagonalOperator(w, sp)
+    ref = sp.from_numpy(np.array(A)).gramian(prod)            # pageable source: plain path
+    V = sp.from_local_numpy(A)
+    assert V.impl._arrivals is not None and len(V.impl._arrivals) > 1
+    G = V.gramian(prod)
+    assert V.impl._arrivals is None
+    np.testing.assert_array_equal(G, G.T)
+    assert O.gram_rel_error(G, ref, A, A, w) < GRAM_TOL
+    assert O.gram_rel_error(G, O.gramian(A, w), A, A, w) < GRAM_TOL
+    for consumer in (lambda X: X.norm(), lambda X: X[3].pairwise_inner(X[5]), lambda X: X.lincomb(np.eye(k)[:, :2]).norm(),
+                     lambda X: X[:5].inner(X[7:9])):
+        X = sp.from_local_numpy(A)
+        got = consumer(X)
+        want = consumer(sp.from_numpy(np.array(A)))
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-13)
+    X = sp.from_local_numpy(A)
+    X[0].axpy(2.0, X[1])
+    np.testing.assert_allclose(X[0].to_numpy()[:, 0], A[:, 0] + 2.0 * A[:, 1], atol=1e-14)
