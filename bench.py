@@ -343,9 +343,13 @@ def run_cuda(args):
                'h2d_bytes_per_step': int(h2d + k * k * 8), 'd2h_bytes_per_step': int(2 * k * k * 8 + 8 * k),
                'ms_per_step': t_e2e, 'steps': n_e2e,
                'host_chunk_columns': k_host,
-               'note': 'snapshots start in pinned host memory and are appended in chunks of host_chunk_columns '
-                       'columns (from_local_numpy + append); H2D of the shard, Gram/check D2H and the '
-                       'coefficient H2D are inside the timed region; the modes stay on the device'}
+               'note': ('snapshots start in pinned host memory; space.from_local_numpy uploads the shard on a copy '
+                        'stream in 8 column blocks and the Gramian contracts the blocks as they land'
+                        if k_host == k else
+                        'snapshots start in pinned host memory and are appended in chunks of host_chunk_columns '
+                        'columns (from_local_numpy + append; N x 80 GB does not fit into host RAM)') +
+                       '; H2D of the shard, Gram/check D2H and the coefficient H2D are inside the timed region; '
+                       'the modes stay on the device'}
         del host_np
     except Exception as exc:                              # e.g. not enough host RAM to pin the shard
         e2e = {'value': None, 'unit': 'TFLOP/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
