@@ -62,11 +62,11 @@ def main():
     V = space.random_device(k, seed=11, scale=1.0 / np.sqrt(n))
     torch.cuda.synchronize()
 
-    def timed(fn):
-        t_end = time.perf_counter() + 0.3                 # warm-up at least 0.3 s: short runs start from idle clocks
-        fn()
-        torch.cuda.synchronize()
-        while time.perf_counter() < t_end:
+    def timed(fn, warm=2):
+        # A FIXED number of warm-up calls: every rank must issue the same sequence of collectives
+        # (a time-based warm-up loop deadlocked the 8-rank run: ranks did different numbers of halo
+        # exchanges).  Short runs start from idle clocks, hence at least two calls.
+        for _ in range(warm):
             fn()
             torch.cuda.synchronize()
         if comm:
@@ -77,12 +77,13 @@ def main():
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / args.reps, out
 
-    l0 = space.ctx.launch_count
     t_proj, P = timed(lambda: alg.project(op, V, V))
-    launches = (space.ctx.launch_count - l0) // (args.reps + 1)
+    l0 = space.ctx.launch_count
+    alg.project(op, V, V)
+    launches = space.ctx.launch_count - l0
     coeff = np.random.default_rng(0).standard_normal((k, 8))
-    t_rec, _ = timed(lambda: V.lincomb(coeff))
-    t_apply, _ = timed(lambda: op.apply(V[:64]))
+    t_rec, _ = timed(lambda: V.lincomb(coeff), warm=5)
+    t_apply, _ = timed(lambda: op.apply(V[:64]), warm=20)
     peak = space.ctx.measure_fp64_peak(True, 200.0)
     nnz = M.nnz
     flop = 2.0 * n * k * k + 2.0 * nnz * k
