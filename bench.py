@@ -12,8 +12,10 @@ block lincomb `A (V / s)` -> orthonormality check (second weighted Gramian).  No
 nothing is cached between steps.  `value` = algorithmic flop / wall time of the whole call (host
 eigensolve included); the per-phase split is reported next to it.
 
-Scaling is WEAK: every rank holds an `--n` x `--k` row shard (global DOFs = N * n), the work per GPU
-is fixed, the only exchange is the all-reduce of the k x k Gram partials.
+Scaling is WEAK by default: every rank holds a `--dofs` x `--k` row shard (global DOFs = N * dofs), the
+work per GPU is fixed, the only exchange is the all-reduce of the k x k Gram partials.
+`--scaling strong` shards a fixed `--dofs` x `--k` problem instead (BASELINE.json config 4 as written); there
+the host eigensolve, which does not shrink with N, bounds the speed-up (Amdahl).
 """
 import argparse
 import json
@@ -186,7 +188,9 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
         comm = ProcessGroupComm()
-    n_local, k = args.n, args.k
+    k = args.k
+    # weak (default): --dofs rows per GPU; strong: --dofs rows in total, split evenly (BASELINE config 4 as written)
+    n_local = args.n if args.scaling == 'weak' else (args.n // world // 16) * 16
     n_global = n_local * world
     space = CudaVectorSpace(n_global, device=device, comm=comm)
     assert space.local_dim == n_local
@@ -368,7 +372,7 @@ def run_cuda(args):
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'TFLOP/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': t_step, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': t_step, 'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': f'POD method_of_snapshots of {n_local} DOF x {k} fp64 snapshots per GPU '
                                    f'({n_global} DOF global), diagonal mass-matrix product, all {m} modes kept',
@@ -393,6 +397,8 @@ def main():
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--dofs', dest='n', type=int, default=10_000_000, help='DOFs per GPU')
     ap.add_argument('--k', type=int, default=1000, help='snapshots')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --dofs per GPU (default); strong: --dofs in total, sharded over the GPUs')
     ap.add_argument('--cpu-sample', type=int, default=150_000, help='rows of the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs)')
