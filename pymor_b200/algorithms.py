@@ -14,6 +14,8 @@ touch raw data, like their reference counterparts):
 * :func:`shifted_chol_qr`       -- src/pymor/algorithms/chol_qr.py:16-252 ("next" row N1: the GEMM-bound
   orthonormalisation -- three Gramians + three block lincombs instead of k^2 dot/axpy pairs with a
   host sync each, i.e. the variant that scales over DOF-sharded GPUs)
+* :func:`inc_vectorarray_hapod` -- src/pymor/algorithms/hapod.py:333 ("next" row N3)
+* :func:`randomized_range_finder` -- src/pymor/algorithms/rand_la.py:20 ("next" row N2, fixed-size mode)
 """
 from __future__ import annotations
 
@@ -268,3 +270,48 @@ def shifted_chol_qr(A, product=None, return_R=False, maxiter=3, offset=0, orth_t
     R[:offset, offset:] = Bi
     R[offset:, offset:] = Ri
     return A, R
+
+
+def inc_vectorarray_hapod(steps, U, eps, omega, product=None):
+    """Incremental hierarchical approximate POD ("next" row N3; reference:
+    src/pymor/algorithms/hapod.py:333-370 over the chain tree of :95-104 with the local tolerances of
+    :414-424): the snapshots are consumed in ``steps`` chunks, each intermediate node is one
+    :func:`pod` of [new chunk, previous modes scaled by their singular values].  Returns
+    ``modes, svals, snap_count``.  Lets POD run on snapshot sets that do not fit HBM at once."""
+    chunk = -(-len(U) // steps)
+    starts = list(range(0, len(U), chunk))
+    levels = len(starts)                       # tree depth - 1 (no POD on the leaves)
+    carried, snap_count = None, 0
+    modes = svals = None
+    for idx, s in enumerate(starts):
+        node = U[s:s + chunk].copy()
+        snap_count += len(node)
+        if carried is not None:
+            node.append(carried, remove_from_other=True)
+        is_root = idx == levels - 1
+        if is_root:
+            tol = np.sqrt(snap_count) * omega * eps
+        else:
+            tol = np.sqrt(snap_count) / np.sqrt(levels - 1) * np.sqrt(1 - omega ** 2) * eps
+        modes, svals = pod(node, product=product, atol=0., rtol=0., l2_err=tol,
+                           orth_tol=1e-10 if is_root else np.inf)
+        if not is_root:
+            modes.scal(svals)
+            carried = modes
+    return modes, svals, snap_count
+
+
+def randomized_range_finder(A, basis_size, power_iterations=0, range_product=None, qr_method='gram_schmidt'):
+    """Orthonormal basis of the (approximate) range of the operator ``A`` from ``basis_size`` random
+    samples ("next" row N2; reference: src/pymor/algorithms/rand_la.py:20-252, fixed-size mode):
+    ``Q = orth(A Omega)``, then ``power_iterations`` times ``Q = orth(A A^T Q)``.  Uses only
+    ``Operator.apply`` / ``apply_adjoint``, ``space.random`` and the orthonormalisation."""
+    def orth(V):
+        if qr_method == 'shifted_chol_qr':
+            return shifted_chol_qr(V, product=range_product, copy=False)
+        return gram_schmidt(V, product=range_product, atol=0., rtol=0., copy=False)
+
+    Q = orth(A.apply(A.source.random(basis_size, distribution='normal')))
+    for _ in range(power_iterations):
+        Q = orth(A.apply(A.apply_adjoint(Q)))
+    return Q

@@ -221,6 +221,26 @@ def chol_qr():
     np.savez_compressed(OUT / 'chol_qr.npz', **out)
 
 
+def hapod():
+    """"Next" row N3: incremental HAPOD (src/pymor/algorithms/hapod.py:333)."""
+    from pymor.algorithms.hapod import inc_vectorarray_hapod
+    from pymor.core.logger import set_log_levels
+    set_log_levels({'pymor': 'WARN'})
+    rng = np.random.default_rng(7)
+    dim, k = 193, 60
+    A = np.asfortranarray(rng.standard_normal((dim, 7)) @ rng.standard_normal((7, k)) * np.sqrt(1.0 / dim)
+                          + 1e-4 * rng.standard_normal((dim, k)))
+    w = rng.uniform(0.5, 1.5, dim)
+    sp = NumpyVectorSpace(dim)
+    out = dict(A=A, w=w)
+    for name, prod in (('euclid', None), ('diag', NumpyMatrixOperator(sps.diags(w).tocsr()))):
+        for steps in (1, 4, 7):
+            modes, svals, count = inc_vectorarray_hapod(steps, sp.from_numpy(A.copy()), 1e-3, 0.75, product=prod)
+            out[f'modes_{name}_{steps}'], out[f'svals_{name}_{steps}'] = modes.to_numpy(), svals
+            assert count == k
+    np.savez_compressed(OUT / 'hapod.npz', **out)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -232,5 +252,6 @@ if __name__ == '__main__':
     projection()
     thermalblock()
     chol_qr()
+    hapod()
     for f in sorted(OUT.glob('*.npz')):
         print(f.name, f.stat().st_size)

@@ -451,3 +451,35 @@ def test_gramian_while_uploading(loaded_lib, rng, monkeypatch):
     X = sp.from_local_numpy(A)
     X[0].axpy(2.0, X[1])
     np.testing.assert_allclose(X[0].to_numpy()[:, 0], A[:, 0] + 2.0 * A[:, 1], atol=1e-14)
+
+
+def test_next_rows_hapod_and_range_finder(loaded_lib, rng):
+    """N3 (incremental HAPOD vs the reference's golden result) and N2 (randomized range finder) on the
+    device through the stand-alone drivers."""
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('hapod')
+    A, w = g['A'], g['w']
+    sp = space_of(A.shape[0])
+    prod = CudaDiagonalOperator(w, sp)
+    for steps in (1, 4, 7):
+        modes, svals, count = alg.inc_vectorarray_hapod(steps, sp.from_numpy(A), 1e-3, 0.75, product=prod)
+        ref_modes, ref_svals = g[f'modes_diag_{steps}'], g[f'svals_diag_{steps}']
+        # the truncation is a threshold decision on a tail sum: allow the count to differ by one
+        assert count == A.shape[1] and abs(len(modes) - ref_modes.shape[1]) <= 1
+        m = min(len(modes), ref_modes.shape[1])
+        np.testing.assert_allclose(svals[:m], ref_svals[:m], rtol=1e-7)
+        assert O.subspace_angle(ref_modes[:, :7], modes.to_numpy()[:, :7], w) < 1e-6      # the 7 signal modes
+    dim = 20011
+    L, Rr = rng.standard_normal((dim, 6)), rng.standard_normal((6, 40))
+    B = L @ Rr                                                    # rank 6, placed in 40 columns of a sparse dim x dim
+    cols = rng.choice(dim, 40, replace=False)
+    rr, cc = np.meshgrid(np.arange(dim), cols, indexing='ij')
+    Mfull = sps.coo_matrix((B.ravel(), (rr.ravel(), cc.ravel())), shape=(dim, dim)).tocsr()
+    sp = space_of(dim)
+    op = CudaCsrOperator(Mfull, sp)
+    Q = alg.randomized_range_finder(op, 10, power_iterations=1)
+    Qh = Q.to_numpy()
+    assert O.orthogonality_error(Qh) < 1e-10
+    resid = L - Qh @ (Qh.T @ L)
+    assert np.linalg.norm(resid) < 1e-8 * np.linalg.norm(L)

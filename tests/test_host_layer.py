@@ -445,3 +445,39 @@ def test_complex_arrays(emu, rng):
     Q, R = alg.gram_schmidt(VA, return_R=True)
     np.testing.assert_allclose(Q.lincomb(R).to_numpy(), A, atol=1e-12)
     np.testing.assert_allclose(Q.gramian(), np.eye(5), atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag'])
+def test_standalone_inc_hapod_golden(emu, name):
+    """"Next" row N3: the stand-alone incremental HAPOD reproduces pyMOR's (mode count, singular
+    values, subspace) for 1, 4 and 7 incremental steps."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    g = load_golden('hapod')
+    A, w = g['A'], g['w']
+    sp = space_of(A.shape[0])
+    W = None if name == 'euclid' else w
+    prod = None if name == 'euclid' else CudaDiagonalOperator(w, sp)
+    for steps in (1, 4, 7):
+        modes, svals, count = alg.inc_vectorarray_hapod(steps, sp.from_numpy(A), 1e-3, 0.75, product=prod)
+        ref_modes, ref_svals = g[f'modes_{name}_{steps}'], g[f'svals_{name}_{steps}']
+        assert count == A.shape[1] and len(modes) == ref_modes.shape[1]
+        np.testing.assert_allclose(svals, ref_svals, rtol=1e-8)
+        assert O.subspace_angle(ref_modes, modes.to_numpy(), W) < 1e-6
+        assert O.orthogonality_error(modes.to_numpy(), W) < 1e-10
+
+
+def test_standalone_randomized_range_finder(emu, rng):
+    """"Next" row N2: the range of a rank-5 operator is captured by 8 random samples."""
+    from pymor_b200.operators import CudaCsrOperator
+    dim = 90
+    L, Rr = rng.standard_normal((dim, 5)), rng.standard_normal((5, dim))
+    M = sps.csr_matrix(L @ Rr)
+    sp = space_of(dim)
+    op = CudaCsrOperator(M, sp)
+    for qr in ('gram_schmidt', 'shifted_chol_qr'):
+        for power in (0, 2):
+            Q = alg.randomized_range_finder(op, 8 if qr == 'gram_schmidt' else 5, power_iterations=power, qr_method=qr)
+            Qh = Q.to_numpy()
+            assert O.orthogonality_error(Qh) < 1e-10
+            Md = M.toarray()
+            assert np.linalg.norm(Md - Qh @ (Qh.T @ Md)) < 1e-8 * np.linalg.norm(Md)
