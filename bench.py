@@ -316,7 +316,14 @@ def run_cuda(args):
         # later chunks (every byte is still copied host -> device inside the timed region).
         avail = psutil_available()
         k_host = int(min(k, max(1, (0.45 * avail / world) // (n_local * 8))))
-        host = torch.empty((k_host, n_local), dtype=torch.float64, pin_memory=True)
+        host = None
+        while host is None:                                # pinning may be limited below the free RAM
+            try:
+                host = torch.empty((k_host, n_local), dtype=torch.float64, pin_memory=True)
+            except RuntimeError:
+                if k_host <= 8:
+                    raise
+                k_host = max(8, k_host // 2)
         host.copy_(A.to_torch()[:k_host])
         del A
         torch.cuda.empty_cache()

@@ -1,0 +1,28 @@
+"""bench.py contract pieces that run without a GPU: the reference arm (oracle port on the host cores)
+prints one well-formed JSON line; the flop model matches SURVEY.md §8d."""
+import json
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def test_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                        '--k', '40', '--dofs', '100000'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['unit'] == 'TFLOP/s' and line['dtype'] == 'f64'
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['vs_baseline'] is None
+
+
+def test_flop_model():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    n, k = 10_000_000, 1000
+    assert bench.pod_flops(n, k, k) == n * k * (k + 1) + 2 * n * k * k + n * k * (k + 1)
+    assert abs(bench.pod_flops(n, k, k) / 4.0e13 - 1) < 0.01          # ~4.0e13 flop
