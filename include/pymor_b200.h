@@ -63,6 +63,12 @@ int pmc_ctx_sync(pmc_ctx *ctx);
 int pmc_ctx_sm_count(pmc_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t pmc_ctx_launch_count(pmc_ctx *ctx);
+/* Tuning switches of the kernels (defaults come from the environment when the context is created):
+ * "gram_opts" (bit set of pymor_b200/csrc/gram2_plan.h; 16 selects the second-generation Gram tile kernel),
+ * "gram_waves" (target CTA waves of the split-n Gram kernel), "csr_variant", "l2_keep".  No reference
+ * counterpart; results do not depend on them beyond the summation order of the Gram partials. */
+int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value);
+int pmc_ctx_get_option(pmc_ctx *ctx, const char *name, int *value);
 /* Pin caller-owned host memory (a shared-memory segment common to the ranks of one box) so that
  * reduction kernels can write their tiny partial results straight into it; *dev_ptr_out is the address
  * to pass as `out`.  The ranks then sum the partials on the host -- the replacement for the

@@ -43,6 +43,8 @@ _CTX_FUNCS = {
     'pmc_measure_fp64_peak': [c_int, c_double, _P],
     'pmc_host_register': [_P, c_size_t, ctypes.POINTER(_P)],
     'pmc_host_unregister': [_P],
+    'pmc_ctx_set_option': [ctypes.c_char_p, c_int],
+    'pmc_ctx_get_option': [ctypes.c_char_p, ctypes.POINTER(c_int)],
 }
 _OTHER_FUNCS = {
     'pmc_version': ([], c_int),
@@ -216,6 +218,16 @@ class DeviceContext:
 
     def unregister_host(self, host_ptr):
         self.lib.pmc_host_unregister(self.handle, host_ptr)
+
+    def set_option(self, name, value):
+        """Kernel tuning switch (``gram_opts``, ``gram_waves``, ``csr_variant``, ``l2_keep``)."""
+        self.flush()
+        self.call('pmc_ctx_set_option', name.encode(), int(value))
+
+    def get_option(self, name):
+        out = c_int(0)
+        self.call('pmc_ctx_get_option', name.encode(), ctypes.byref(out))
+        return int(out.value)
 
     def measure_fp64_peak(self, use_dmma=True, ms=200.0):
         out = np.zeros(1)

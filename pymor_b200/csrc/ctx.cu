@@ -96,6 +96,32 @@ extern "C" int pmc_ctx_sync(pmc_ctx *ctx) {
     return PMC_OK;
 }
 
+// Tuning switches, initialised from the environment at context creation (PMC_GRAM_OPTS, PMC_GRAM_WAVES,
+// PMC_CSR_VARIANT, PMC_NO_L2_KEEP); settable at run time so that one process can A/B kernel variants.
+static int *pmc_option_slot(pmc_ctx *ctx, const char *name) {
+    if (!ctx || !name) return nullptr;
+    if (!strcmp(name, "gram_opts")) return &ctx->gram_opts;
+    if (!strcmp(name, "gram_waves")) return &ctx->gram_waves;
+    if (!strcmp(name, "csr_variant")) return &ctx->csr_variant;
+    if (!strcmp(name, "l2_keep")) return &ctx->l2_keep;
+    return nullptr;
+}
+
+extern "C" int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value) {
+    int *slot = pmc_option_slot(ctx, name);
+    PMC_REQUIRE(slot != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep)");
+    PMC_REQUIRE(slot != &ctx->gram_waves || value > 0, "gram_waves must be positive");
+    *slot = value;
+    return PMC_OK;
+}
+
+extern "C" int pmc_ctx_get_option(pmc_ctx *ctx, const char *name, int *value) {
+    int *slot = pmc_option_slot(ctx, name);
+    PMC_REQUIRE(slot != nullptr && value != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep)");
+    *value = *slot;
+    return PMC_OK;
+}
+
 extern "C" int pmc_ctx_sm_count(pmc_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" int64_t pmc_ctx_launch_count(pmc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -10,6 +10,8 @@
 //
 // Algorithmic work: 2*n*kA*kB flop (n*k*(k+1) for SYRK), 8*n*(kA+kB) bytes (8*n*k for SYRK).
 #include "common.cuh"
+#include "gram2_plan.h"
+#include "gram_params.cuh"
 
 namespace {
 
@@ -23,28 +25,6 @@ constexpr int TILE_ELEMS = BM * BK;               // 2048 doubles = 16 KB
 constexpr uint32_t TILE_BYTES = TILE_ELEMS * 8;
 constexpr size_t GRAM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * (2 * TILE_BYTES + BK * 8) +
                              2 * STAGES * sizeof(uint64_t) + 64;
-
-struct GramParams {
-    int64_t n;
-    int64_t rows_per_split;   // multiple of BK
-    int tiles_m, tiles_n, ntiles;
-    int symmetric;
-    int kA, kB;
-    int opts;                 // ablation switches (env PMC_GRAM_OPTS): 1 no diag skip, 2 no empty-block skip, 4 no transpose
-    double *partials;         // [item][BN][BM]
-};
-
-__device__ __forceinline__ void decode_tile(const GramParams &p, int tile, int &ti, int &tj) {
-    if (p.symmetric) {
-        int rem = tile;
-        tj = 0;
-        while (rem >= p.tiles_m - tj) { rem -= p.tiles_m - tj; ++tj; }
-        ti = tj + rem;
-    } else {
-        ti = tile % p.tiles_m;
-        tj = tile / p.tiles_m;
-    }
-}
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
@@ -348,6 +328,12 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
             if (rc) return rc;
         } else {
             tmW = tmA;
+        }
+        if (p.opts & G2_OPT_ENABLE) {
+            // second-generation tile kernel with its own reduction (gram2.cu)
+            rc = pmc_gram2_launch(ctx, tmA, tmB, tmW, p, items, nsplit, w != nullptr, out, ldo, accumulate);
+            if (rc) return rc;
+            return pmc_after_launch(ctx, 2, flags);
         }
         if (w) {
             PMC_CHECK_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<true>,

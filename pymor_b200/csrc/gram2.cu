@@ -1,0 +1,258 @@
+// gram2_dmma_kernel -- second generation of the tall-skinny Gram / SYRK tile kernel (gram.cu holds the
+// first one and the generic kernels).  Same tiling and pipeline (128x128 partial tile per CTA in
+// registers, [128 col x 16 row] 128B-swizzled TMA boxes, 6-stage mbarrier ring, mma.sync m8n8k4.f64 =
+// DMMA.8x8x4), selected with bit 16 of ctx->gram_opts (env PMC_GRAM_OPTS / pmc_ctx_set_option) until it
+// has been measured against gram_dmma_kernel on a B200.  What it changes, all on the FP64 tensor pipe
+// that bounds this kernel (round-1 numbers: 128-tile quantisation and diagonal tiles cost 10 %, the
+// diagonal weight 6-7 %):
+//
+//  * diagonal SYRK tiles: the four diagonal 32x32 blocks compute only the 10 of 16 sub-blocks on/below
+//    the diagonal, two off-diagonal blocks are K-split over two warps each, so every SMSP carries
+//    2.125 block units (a full tile: 4; gram_dmma_kernel: 3);
+//  * partially filled blocks (k not a multiple of 32) run only their 8-row / 8-column sub-blocks that
+//    hold data, through compile-time specialisations of the stage loop (no predicated DMMA), and are
+//    spread over the four SMSPs;
+//  * the diagonal weight is applied ONCE per stage in shared memory (each warp scales 1/16 of the B tile
+//    three stages ahead: 4 DMUL per warp and stage) instead of on every warp's fragments (16 DMUL per
+//    warp and stage).  For diagonal tiles the scaled copy goes to the B slot the tile does not load.
+//    Products round exactly as in gram_dmma_kernel (fl(w*b) first), so unsplit blocks are bitwise equal.
+//
+// The index maps live in gram2_plan.h and are checked on the CPU by tests/native/gram2_model.cpp.
+#include "common.cuh"
+#include "gram2_plan.h"
+#include "gram_params.cuh"
+
+namespace {
+
+constexpr int BM = G2_BM, BN = G2_BN, BK = G2_BK;
+constexpr int STAGES = 6;
+constexpr int LOOKAHEAD = 3;                      // weight scaling runs this many stages ahead of the MMA
+constexpr int THREADS = 32 * G2_WARPS;
+constexpr int TILE_ELEMS = G2_TILE_ELEMS;
+constexpr uint32_t TILE_BYTES = TILE_ELEMS * 8;
+constexpr size_t GRAM2_SMEM = 1024 /*align slack*/ + (size_t)STAGES * (2 * TILE_BYTES + BK * 8) +
+                              3 * STAGES * sizeof(uint64_t) + 64;
+
+// One stage (16 rows = KS quarter-steps of 4) of a warp's block.  NM x NN sub-blocks of 8x8; TRI keeps
+// the sub-blocks with ni <= mi.  `fo` holds the fragment offsets of the warp's quarter-steps.
+template <int NM, int NN, bool TRI, int KS>
+__device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *a_s, const double *b_s,
+                                          const int (&fo)[4]) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        double a[NM], b[NN];
+#pragma unroll
+        for (int mi = 0; mi < NM; ++mi) a[mi] = a_s[mi * 8 * BK + fo[ks]];
+#pragma unroll
+        for (int ni = 0; ni < NN; ++ni) b[ni] = b_s[ni * 8 * BK + fo[ks]];
+#pragma unroll
+        for (int mi = 0; mi < NM; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NN; ++ni)
+                if (!TRI || ni <= mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+
+// shape codes of the warp-uniform dispatch in the stage loop
+constexpr int SHAPE_IDLE = -1, SHAPE_TRI = 32, SHAPE_HALF = 64;   // rectangular: (nm-1)*4 + (nn-1)
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(THREADS, 1)
+gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmW, const GramParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // 1024B alignment: the 128B swizzle pattern is a function of the absolute smem address
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    double *sA = reinterpret_cast<double *>(smem);
+    double *sB = sA + STAGES * TILE_ELEMS;
+    double *sW = sB + STAGES * TILE_ELEMS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sW + STAGES * BK);
+    uint64_t *empty = full + STAGES;
+    uint64_t *ready = empty + STAGES;               // WEIGHTED: stage has been scaled by all warps
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const int item = blockIdx.x;
+    const int tile = item % p.ntiles, split = item / p.ntiles;
+    int ti, tj;
+    decode_tile(p, tile, ti, tj);
+    const bool diag = p.symmetric && ti == tj;
+    const int64_t r0 = (int64_t)split * p.rows_per_split;
+    const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
+    const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
+
+    const int vm = min(BM, p.kA - ti * BM), vn = min(BN, p.kB - tj * BN);   // valid rows / cols of this tile
+    const G2Plan plan = g2_plan(warp, diag, vm, vn, p.opts);
+    const int shape = !plan.active ? SHAPE_IDLE
+                      : plan.tri   ? SHAPE_TRI + plan.nm - 1
+                      : plan.nks == 2 ? SHAPE_HALF
+                                      : (plan.nm - 1) * 4 + (plan.nn - 1);
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (WEIGHTED) tma_prefetch_desc(&tmW);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], G2_WARPS);
+            mbar_init(&ready[s], G2_WARPS);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const uint32_t stage_bytes = TILE_BYTES * (diag ? 1u : 2u) + (WEIGHTED ? BK * 8u : 0u);
+    auto issue = [&](int kt) {
+        const int s = kt % STAGES;
+        const int32_t d = (int32_t)(r0 + (int64_t)kt * BK);
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        tma_load_2d(sA + s * TILE_ELEMS, &tmA, &full[s], d, ti * BM);
+        if (!diag) tma_load_2d(sB + s * TILE_ELEMS, &tmB, &full[s], d, tj * BN);
+        if (WEIGHTED) tma_load_1d(sW + s * BK, &tmW, &full[s], d);
+    };
+    if (tid == 0) {
+        const int pre = nk < STAGES ? nk : STAGES;
+        for (int kt = 0; kt < pre; ++kt) issue(kt);
+    }
+
+    // WEIGHTED: B tile of stage kt *= w (rows of the stage), written to the B slot -- in place for
+    // off-diagonal tiles, from the A slot for diagonal tiles (which load one operand only).  Every warp
+    // scales its 8 tile rows, then arrives on ready[stage].
+    int sc_elem[2], sc_w[2];
+    g2_scale_slice(warp, lane, 0, sc_elem[0], sc_w[0]);
+    g2_scale_slice(warp, lane, 1, sc_elem[1], sc_w[1]);
+    auto scale_stage = [&](int kt) {
+        const int s = kt % STAGES;
+        mbar_wait(&full[s], (kt / STAGES) & 1);
+        const double *src = (diag ? sA : sB) + s * TILE_ELEMS;
+        double *dst = sB + s * TILE_ELEMS;
+        const double *wv = sW + s * BK;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            double2 v = *reinterpret_cast<const double2 *>(src + sc_elem[part]);
+            const double2 ww = *reinterpret_cast<const double2 *>(wv + sc_w[part]);
+            v.x *= ww.x;
+            v.y *= ww.y;
+            *reinterpret_cast<double2 *>(dst + sc_elem[part]) = v;
+        }
+        fence_proxy_async();          // these generic-proxy writes precede the TMA refill of the slot
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+    };
+    if (WEIGHTED) {
+        const int pre = nk < LOOKAHEAD ? nk : LOOKAHEAD;
+        for (int kt = 0; kt < pre; ++kt) scale_stage(kt);
+    }
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    int fo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fo[i] = g2_frag_offset((plan.ks0 + i) & 3, lane);
+    const int rho = g2_rho(lane >> 2);
+    const int rowA = (plan.wm * 32 + rho) * BK;
+    const int rowB = (plan.wn * 32 + rho) * BK;
+    const double *b_base = (diag && !WEIGHTED) ? sA : sB;
+
+    for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % STAGES;
+        // producer: refill the stage everybody released one iteration ago
+        if (tid == 0 && kt >= 1 && kt - 1 + STAGES < nk) {
+            const int sp = (kt - 1) % STAGES;
+            mbar_wait(&empty[sp], ((kt - 1) / STAGES) & 1);
+            issue(kt - 1 + STAGES);
+        }
+        mbar_wait(WEIGHTED ? &ready[s] : &full[s], (kt / STAGES) & 1);
+        const double *a_s = sA + s * TILE_ELEMS + rowA;
+        const double *b_s = b_base + s * TILE_ELEMS + rowB;
+        switch (shape) {
+#define G2_RECT(NM, NN) \
+    case (NM - 1) * 4 + (NN - 1): stage_mma<NM, NN, false, 4>(acc, a_s, b_s, fo); break;
+            G2_RECT(4, 4) G2_RECT(4, 3) G2_RECT(4, 2) G2_RECT(4, 1)
+            G2_RECT(3, 4) G2_RECT(3, 3) G2_RECT(3, 2) G2_RECT(3, 1)
+            G2_RECT(2, 4) G2_RECT(2, 3) G2_RECT(2, 2) G2_RECT(2, 1)
+            G2_RECT(1, 4) G2_RECT(1, 3) G2_RECT(1, 2) G2_RECT(1, 1)
+#undef G2_RECT
+            case SHAPE_TRI + 3: stage_mma<4, 4, true, 4>(acc, a_s, b_s, fo); break;
+            case SHAPE_TRI + 2: stage_mma<3, 3, true, 4>(acc, a_s, b_s, fo); break;
+            case SHAPE_TRI + 1: stage_mma<2, 2, true, 4>(acc, a_s, b_s, fo); break;
+            case SHAPE_TRI + 0: stage_mma<1, 1, true, 4>(acc, a_s, b_s, fo); break;
+            case SHAPE_HALF: stage_mma<4, 4, false, 2>(acc, a_s, b_s, fo); break;
+            default: break;
+        }
+        if (WEIGHTED && kt + LOOKAHEAD < nk) scale_stage(kt + LOOKAHEAD);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // epilogue: partial tile, column-major [j][i]; sub-blocks nobody reads later are not written
+    if (plan.active) {
+        double *out = p.partials + (size_t)item * (BM * BN);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                if (mi >= plan.nm || ni >= plan.nn || (plan.tri && ni > mi)) continue;
+                out[g2_out_index(plan, mi, ni, lane, 0)] = acc[mi][ni][0];
+                out[g2_out_index(plan, mi, ni, lane, 1)] = acc[mi][ni][1];
+            }
+    }
+}
+
+// stage 2: out[i + j*ldo] = sum_split partial[split][tile][j][i]  (+ the mirrored K-half of split blocks,
+// + mirror for SYRK).  Fixed order => bitwise reproducible.
+__global__ void gram2_reduce_kernel(const double *__restrict__ partials, int nsplit, GramParams p,
+                                    double *__restrict__ out, int64_t ldo, int accumulate) {
+    const int tile = blockIdx.y;
+    int ti, tj;
+    decode_tile(p, tile, ti, tj);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= BM * BN) return;
+    const int il = e % BM, jl = e / BM;
+    const int gi = ti * BM + il, gj = tj * BN + jl;
+    if (gi >= p.kA || gj >= p.kB) return;
+    const bool diag = p.symmetric && ti == tj;
+    if (diag && gi < gj) return;                    // strictly-upper part of diagonal tiles: mirrored
+    const size_t tile_elems = (size_t)BM * BN;
+    const double *src = partials + (size_t)tile * tile_elems;
+    const size_t step = (size_t)p.ntiles * tile_elems;
+    const int vm = min(BM, p.kA - ti * BM);
+    const bool two = diag && g2_is_split_block(il >> 5, jl >> 5, vm, p.opts);
+    const int e2 = two ? g2_mirror_index(il, jl) : e;
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) {
+        double v = src[(size_t)sp * step + e];
+        if (two) v += src[(size_t)sp * step + e2];
+        s += v;
+    }
+    if (accumulate) s += out[gi + (int64_t)gj * ldo];
+    out[gi + (int64_t)gj * ldo] = s;
+    if (p.symmetric && gi != gj) out[gj + (int64_t)gi * ldo] = s;
+}
+
+}  // namespace
+
+// Launch of the tile kernel + reduction on behalf of pmc_gram_impl (which has validated the operands,
+// chosen the split and encoded the tensor maps).  Two launches.
+int pmc_gram2_launch(pmc_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmW,
+                     const GramParams &p, int64_t items, int64_t nsplit, bool weighted, double *out,
+                     int64_t ldo, int accumulate) {
+    if (weighted) {
+        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)GRAM2_SMEM));
+        gram2_dmma_kernel<true><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+    } else {
+        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)GRAM2_SMEM));
+        gram2_dmma_kernel<false><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+    }
+    PMC_CHECK_CUDA(cudaGetLastError());
+    dim3 rgrid((BM * BN + 255) / 256, p.ntiles);
+    gram2_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(p.partials, (int)nsplit, p, out, ldo, accumulate);
+    return PMC_OK;
+}

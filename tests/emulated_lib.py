@@ -69,6 +69,18 @@ class EmulatedLib:
     def pmc_ctx_launch_count(self, ctx):
         return self.launches
 
+    def pmc_ctx_set_option(self, ctx, name, value):
+        if name not in (b'gram_opts', b'gram_waves', b'csr_variant', b'l2_keep'):
+            self._err = b'unknown option'
+            return PMC_ERR_INVALID
+        self.options = getattr(self, 'options', {})
+        self.options[name] = int(value)
+        return PMC_OK
+
+    def pmc_ctx_get_option(self, ctx, name, out):
+        out._obj.value = getattr(self, 'options', {}).get(name, 0)
+        return PMC_OK
+
     def pmc_host_register(self, ctx, host_ptr, nbytes, out):
         out._obj.value = int(host_ptr)
         return PMC_OK

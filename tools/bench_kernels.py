@@ -33,6 +33,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--shapes', default='2000000x500,10000000x1000,4000000x256,1000000x2000')
     ap.add_argument('--reps', type=int, default=3)
+    ap.add_argument('--opts', default=os.environ.get('PMC_GRAM_OPTS', '0'),
+                    help='comma-separated gram_opts values to A/B in one process (csrc/gram2_plan.h; 16 = gram2 kernel)')
+    ap.add_argument('--no-lincomb', action='store_true')
     args = ap.parse_args()
     peak = None
     for shape in args.shapes.split(','):
@@ -46,20 +49,25 @@ def main():
         out = torch.empty(k * k, device='cuda', dtype=torch.float64)
         impl = A.impl
         pa, cs = impl._ptr(0), impl.ld
-        res = {'shape': shape, 'dmma_peak_tflops': peak, 'gram_opts': os.environ.get('PMC_GRAM_OPTS', '0')}
-        for name, wp, flags, flop in (('syrk', 0, PMC_SYMMETRIC, n * k * (k + 1.0)),
-                                      ('syrk_w', w.data_ptr(), PMC_SYMMETRIC, n * k * (k + 1.0)),
-                                      ('gemm_w', w.data_ptr(), 0, 2.0 * n * k * k)):
-            ms = timed(lambda: ctx.call('pmc_gram', pa, cs, k, pa, cs, k, n, wp, out.data_ptr(), k, flags), args.reps)
-            res[name] = {'ms': ms, 'tflops': flop / ms * 1e-9, 'frac': flop / ms * 1e-9 / peak}
-        if 2 * n * k * 8 < 150e9:
+        for opts in (int(v) for v in args.opts.split(',')):
+            ctx.set_option('gram_opts', opts)
+            res = {'shape': shape, 'dmma_peak_tflops': peak, 'gram_opts': opts}
+            for name, wp, flags, flop in (('syrk', 0, PMC_SYMMETRIC, n * k * (k + 1.0)),
+                                          ('syrk_w', w.data_ptr(), PMC_SYMMETRIC, n * k * (k + 1.0)),
+                                          ('gemm_w', w.data_ptr(), 0, 2.0 * n * k * k)):
+                ms = timed(lambda: ctx.call('pmc_gram', pa, cs, k, pa, cs, k, n, wp, out.data_ptr(), k, flags), args.reps)
+                res[name] = {'ms': ms, 'tflops': flop / ms * 1e-9, 'frac': flop / ms * 1e-9 / peak}
+            print(json.dumps(res), flush=True)
+        ctx.set_option('gram_opts', 0)
+        res = {'shape': shape, 'dmma_peak_tflops': peak}
+        if 2 * n * k * 8 < 150e9 and not args.no_lincomb:
             C = torch.randn((k, k), device='cuda', dtype=torch.float64)
             R = sp.zeros(k)
             ms = timed(lambda: ctx.call('pmc_lincomb', pa, cs, k, n, C.data_ptr(), k, k, R.impl._ptr(0), R.impl.ld, 0),
                        args.reps)
             res['lincomb'] = {'ms': ms, 'tflops': 2.0 * n * k * k / ms * 1e-9, 'frac': 2.0 * n * k * k / ms * 1e-9 / peak}
             del R, C
-        print(json.dumps(res))
+            print(json.dumps(res), flush=True)
         del A, impl, w, out
         torch.cuda.empty_cache()
 
