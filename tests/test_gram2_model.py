@@ -128,3 +128,116 @@ def test_fragment_loads_are_bank_conflict_free_and_scaling_covers_the_tile(model
                 assert elems[8 * q:8 * q + 8] == list(range(elems[8 * q], elems[8 * q] + 16, 2))
                 assert elems[8 * q] % 16 == 0
     assert (seen == 1).all()
+
+
+# ------------------------------------------------------------------------------------------------------
+# mbarrier protocol of gram2_dmma_kernel<WEIGHTED> as a randomly scheduled discrete-event simulation
+# ------------------------------------------------------------------------------------------------------
+class _MBar:
+    def __init__(self, count):
+        self.count, self.pending, self.phase = count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0
+        if self.pending == 0:
+            self.pending, self.phase = self.count, self.phase + 1
+
+    def done(self, parity):            # mbarrier.try_wait.parity: has the phase with this parity completed?
+        return (self.phase & 1) != parity
+
+
+def _simulate_protocol(nk, weighted, diag, rnd, stages=6, look=3, warps=16):
+    full = [_MBar(1) for _ in range(stages)]
+    empty = [_MBar(warps) for _ in range(stages)]
+    ready = [_MBar(warps) for _ in range(stages)]
+    slotA, slotB = [None] * stages, [None] * stages     # stage index the slot holds
+    scaled = [set() for _ in range(nk)]                  # warps that scaled stage kt
+    computed = [set() for _ in range(nk)]
+    in_flight = []                                       # TMA loads issued, not landed
+
+    def issue(kt):
+        in_flight.append(kt)
+
+    def land(kt):
+        s = kt % stages
+        if kt >= stages:                                 # the slot's previous stage must be dead
+            assert len(computed[kt - stages]) == warps
+            assert not weighted or len(scaled[kt - stages]) == warps
+        slotA[s] = kt
+        if not diag:
+            slotB[s] = ('raw', kt)
+        full[s].arrive()
+
+    def scale(w, kt):
+        s = kt % stages
+        yield lambda: full[s].done((kt // stages) & 1)
+        assert slotA[s] == kt
+        if diag:                                         # scaled copy goes to the B slot: its old readers are done
+            assert kt < stages or len(computed[kt - stages]) == warps
+        else:
+            assert slotB[s] in (('raw', kt), ('scaled', kt))
+        slotB[s] = ('scaled', kt)
+        assert w not in scaled[kt]
+        scaled[kt].add(w)
+        ready[s].arrive()
+
+    def warp_program(w):
+        if w == 0:
+            for kt in range(min(nk, stages)):
+                issue(kt)
+        if weighted:
+            for kt in range(min(nk, look)):
+                yield from scale(w, kt)
+        for kt in range(nk):
+            s = kt % stages
+            if w == 0 and kt >= 1 and kt - 1 + stages < nk:
+                sp = (kt - 1) % stages
+                yield lambda: empty[sp].done(((kt - 1) // stages) & 1)
+                issue(kt - 1 + stages)
+            bar = ready[s] if weighted else full[s]
+            yield lambda: bar.done((kt // stages) & 1)
+            assert slotA[s] == kt
+            if weighted:
+                assert len(scaled[kt]) == warps and slotB[s] == ('scaled', kt)
+            elif not diag:
+                assert slotB[s] == ('raw', kt)
+            computed[kt].add(w)
+            yield lambda: True                            # the MMA takes a while: let others run
+            if weighted and kt + look < nk:
+                yield from scale(w, kt + look)
+            empty[s].arrive()
+
+    progs = {w: warp_program(w) for w in range(warps)}
+    waiting = {}
+    for w, g in list(progs.items()):
+        try:
+            waiting[w] = next(g)
+        except StopIteration:
+            del progs[w]
+    steps = 0
+    while progs or in_flight:
+        steps += 1
+        assert steps < 10_000_000
+        choices = [('warp', w) for w in progs if waiting[w]()] + [('tma', i) for i in range(len(in_flight))]
+        assert choices, f'deadlock: warps {sorted(progs)} blocked, nothing in flight'
+        kind, x = choices[rnd.integers(len(choices))]
+        if kind == 'tma':
+            land(in_flight.pop(x))
+        else:
+            try:
+                waiting[x] = next(progs[x])
+            except StopIteration:
+                del progs[x], waiting[x]
+    assert all(len(c) == warps for c in computed)
+
+
+@pytest.mark.parametrize('weighted', [False, True])
+@pytest.mark.parametrize('diag', [False, True])
+def test_barrier_protocol_simulation(rng, weighted, diag):
+    """Random interleavings of the 16 warps and the TMA completions: no deadlock, no phase aliasing (a
+    parity wait never passes on a stale phase), every stage is scaled exactly once by every warp before
+    anybody multiplies it, and no slot is overwritten (by TMA or by the scaling) while it still has readers."""
+    for nk in (1, 2, 3, 4, 6, 7, 13, 40):
+        for _ in range(6):
+            _simulate_protocol(nk, weighted, diag, rng)
