@@ -334,6 +334,88 @@ def shifted_chol_qr(A, W=None, return_R=False, maxiter=3, offset=0, product_norm
 # ------------------------------------------------------------------------------------------------
 # parity metrics named by the north star
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# empirical interpolation ("next" row N5; src/pymor/algorithms/ei.py)
+# ------------------------------------------------------------------------------------------------
+def ei_greedy(U, error_norm=None, atol=None, rtol=None, max_interpolation_dofs=None, nodal_basis=False):
+    """EI-greedy (ei.py:30-179) on a (dim, len) matrix; ``error_norm`` None (Euclidean) or 'sup'.
+    Returns interpolation DOFs, collateral basis (dim, m) and the data dict of the reference."""
+    U = np.array(U, order='F', dtype=float)
+    k = U.shape[1]
+    measure = (lambda E: np.max(np.abs(E), axis=0)) if error_norm == 'sup' else (lambda E: norm(E))
+    picked, basis = [], np.zeros((U.shape[0], 0), order='F')
+    K, coefficients = np.eye(k), np.zeros((k, 0))
+    max_errs = []
+    errs = measure(U)                                                       # :114
+    worst = int(np.argmax(errs))
+    first_err = err = errs[worst]
+    while True:
+        if max_interpolation_dofs is not None and len(picked) >= max_interpolation_dofs:   # :120
+            break
+        if atol is not None and err <= atol:                                # :129
+            break
+        if rtol is not None and err / first_err <= rtol:                    # :133
+            break
+        vec = U[:, worst].copy()                                            # :138
+        dof = int(amax(vec[:, None])[0][0])
+        if dof in picked:                                                   # :140
+            break
+        pivot = vec[dof]
+        if pivot == 0.:                                                     # :144
+            break
+        vec *= 1 / pivot                                                    # :147
+        picked.append(dof)
+        basis = np.asfortranarray(np.hstack([basis, vec[:, None]]))
+        coefficients = np.hstack([coefficients, K[:, worst:worst + 1] / pivot])
+        max_errs.append(err)
+        row = U[dof:dof + 1, :].copy()                                      # :154  U.dofs([dof])
+        U = axpy(U, -row[0], vec[:, None])                                  # :155
+        K -= K[:, worst:worst + 1] @ (row / pivot)
+        errs = measure(U)
+        worst = int(np.argmax(errs))
+        err = errs[worst]
+    dofs_ = np.array(picked, dtype=np.int64)
+    matrix = dofs(basis, dofs_)                                             # :161
+    tri = np.abs(matrix - np.tril(matrix))
+    tri_errs = [np.max(tri[:d, :d]) for d in range(1, len(matrix) + 1)]
+    if nodal_basis:                                                         # :169-174
+        inv = spla.inv(matrix)
+        basis = lincomb(basis, inv)
+        coefficients = coefficients @ inv
+        matrix = np.eye(basis.shape[1])
+    return dofs_, basis, {'errors': max_errs, 'triangularity_errors': tri_errs, 'coefficients': coefficients,
+                          'interpolation_matrix': matrix}
+
+
+def deim(U, W=None, modes=None, use_pod=True, atol=None, rtol=None):
+    """DEIM (ei.py:182-264): POD of the snapshots (reference defaults: ``qr_svd``), then one interpolation DOF per
+    mode at the largest entry of its interpolation residual."""
+    data = {}
+    if use_pod:
+        kw = {}
+        if atol is not None:
+            kw['atol'] = atol
+        if rtol is not None:
+            kw['rtol'] = rtol
+        basis, svals = pod(np.asarray(U), W, modes=modes, method='qr_svd', **kw)   # :229
+        data['svals'] = svals
+    else:
+        basis = np.array(U, order='F', dtype=float)
+    picked, matrix = [], np.zeros((0, 0))
+    for i in range(basis.shape[1]):
+        if picked:                                                          # :241-245
+            coeff = spla.solve(matrix, basis[picked, i])
+            resid = basis[:, i] - basis[:, :len(picked)] @ coeff
+        else:
+            resid = basis[:, i]
+        dof = int(amax(resid[:, None])[0][0])                               # :250
+        if dof in picked:
+            break
+        picked.append(dof)
+        matrix = dofs(basis[:, :len(picked)], picked)                       # :257
+    return np.array(picked, dtype=np.int64), np.asfortranarray(basis[:, :len(picked)]), data
+
+
 def subspace_angle(U, V, W=None):
     """Largest principal angle between span(U) and span(V) (columns W-orthonormal)."""
     if U.shape[1] == 0 and V.shape[1] == 0:

@@ -16,6 +16,8 @@ touch raw data, like their reference counterparts):
   host sync each, i.e. the variant that scales over DOF-sharded GPUs)
 * :func:`inc_vectorarray_hapod` -- src/pymor/algorithms/hapod.py:333 ("next" row N3)
 * :func:`randomized_range_finder` -- src/pymor/algorithms/rand_la.py:20 ("next" row N2, fixed-size mode)
+* :func:`ei_greedy`, :func:`deim` -- src/pymor/algorithms/ei.py:30, :182 ("next" row N5: empirical
+  interpolation data; the backend sees ``amax`` / ``dofs`` / per-column ``axpy`` / ``norm`` / ``lincomb``)
 """
 from __future__ import annotations
 
@@ -315,3 +317,110 @@ def randomized_range_finder(A, basis_size, power_iterations=0, range_product=Non
     for _ in range(power_iterations):
         Q = orth(A.apply(A.apply_adjoint(Q)))
     return Q
+
+
+def ei_greedy(U, error_norm=None, atol=None, rtol=None, max_interpolation_dofs=None, nodal_basis=False,
+              copy=True):
+    """Interpolation DOFs and collateral basis by the EI-greedy search ("next" row N5; reference:
+    src/pymor/algorithms/ei.py:30-179, sequential branch).  In every round the worst approximated
+    vector becomes a basis vector, normalised to 1 at its largest entry (the new interpolation DOF),
+    and is eliminated from all vectors at that DOF.  Per round the backend runs one ``amax``, two
+    ``dofs``, one ``axpy`` with per-column coefficients over the whole array (24 n k bytes) and one
+    ``norm`` / ``sup_norm`` (8 n k bytes): HBM-bound, one host sync per reduction.
+
+    ``error_norm``: ``None`` (Euclidean), ``'sup'`` or a callable ``VectorArray -> ndarray``.
+    Returns ``interpolation_dofs, collateral_basis, data`` with the reference's ``data`` keys."""
+    assert not isinstance(error_norm, str) or error_norm == 'sup'
+    assert len(U) > 0
+    if error_norm is None:
+        def measure(V):
+            return V.norm()
+    elif error_norm == 'sup':
+        def measure(V):
+            return V.sup_norm()
+    else:
+        measure = error_norm
+    k = len(U)
+    dofs = np.zeros((0,), dtype=np.int32)
+    basis = U.space.empty()
+    K = np.eye(k)                                  # U_current = U_initial.lincomb(K)
+    coefficients = np.zeros((k, 0))
+    max_errs = []
+    if copy:
+        U = U.copy()
+    errs = measure(U)
+    worst = int(np.argmax(errs))
+    first_err = err = errs[worst]
+    while True:
+        if max_interpolation_dofs is not None and len(dofs) >= max_interpolation_dofs:
+            logger.info('Maximum number of interpolation DOFs reached (error %g)', err)
+            break
+        if atol is not None and err <= atol:
+            break
+        if rtol is not None and err / first_err <= rtol:
+            break
+        vec = U[worst].copy()
+        dof = vec.amax()[0][0]
+        if dof in dofs:
+            logger.info('DOF %d selected twice for interpolation, stopping', dof)
+            break
+        pivot = vec.dofs([dof])[0, 0]
+        if pivot == 0.:
+            logger.info('DOF %d selected for interpolation has zero maximum error, stopping', dof)
+            break
+        vec.scal(1 / pivot)
+        dofs = np.hstack((dofs, dof))
+        basis.append(vec)
+        coefficients = np.hstack([coefficients, K[:, worst:worst + 1] / pivot])
+        max_errs.append(err)
+        row = U.dofs([dof])
+        U.axpy(-row[0, :], vec)
+        K -= K[:, worst:worst + 1] @ (row / pivot)
+        errs = measure(U)
+        worst = int(np.argmax(errs))
+        err = errs[worst]
+    matrix = basis.dofs(dofs)
+    tri = np.abs(matrix - np.tril(matrix))
+    tri_errs = [np.max(tri[:d, :d]) for d in range(1, len(matrix) + 1)]
+    if nodal_basis:
+        inv = spla.inv(matrix)
+        basis = basis.lincomb(inv)
+        coefficients = coefficients @ inv
+        matrix = np.eye(len(basis))
+    return dofs, basis, {'errors': max_errs, 'triangularity_errors': tri_errs, 'coefficients': coefficients,
+                         'interpolation_matrix': matrix}
+
+
+def deim(U, modes=None, pod=True, atol=None, rtol=None, product=None, pod_options={}):
+    """Interpolation DOFs and collateral basis by DEIM ("next" row N5; reference:
+    src/pymor/algorithms/ei.py:182-264): POD of ``U`` (unless ``pod=False``), then for every mode the
+    DOF where its interpolation residual w.r.t. the previous modes is largest.  Returns
+    ``interpolation_dofs, collateral_basis, data`` (``data['svals']`` when the POD ran)."""
+    data = {}
+    if pod:
+        kw = dict(pod_options)
+        if atol is not None:
+            kw['atol'] = atol
+        if rtol is not None:
+            kw['rtol'] = rtol
+        basis, svals = globals()['pod'](U, modes=modes, product=product, **kw)
+        data['svals'] = svals
+    else:
+        basis = U
+    dofs = np.zeros((0,), dtype=np.int32)
+    matrix = np.zeros((0, 0))
+    for i in range(len(basis)):
+        if len(dofs) > 0:
+            coeff = spla.solve(matrix, basis[i].dofs(dofs))
+            resid = basis[i] - basis[:len(dofs)].lincomb(coeff)
+        else:
+            resid = basis[i]
+        dof = resid.amax()[0][0]
+        if dof in dofs:
+            logger.info('DOF %d selected twice for interpolation, stopping', dof)
+            break
+        dofs = np.hstack((dofs, dof))
+        matrix = basis[:len(dofs)].dofs(dofs)
+    if len(dofs) < len(basis):
+        del basis[len(dofs):len(basis)]
+    return dofs, basis, data

@@ -241,6 +241,35 @@ def hapod():
     np.savez_compressed(OUT / 'hapod.npz', **out)
 
 
+def ei():
+    """"Next" row N5: empirical interpolation data, EI-greedy and DEIM (src/pymor/algorithms/ei.py:30, :182):
+    amax / dofs / vector-alpha axpy / norm / lincomb on the backend, the small solves on the host."""
+    from pymor.algorithms.ei import deim, ei_greedy
+    from pymor.core.logger import set_log_levels
+    set_log_levels({'pymor': 'WARN'})
+    rng = np.random.default_rng(11)
+    dim, k = 211, 30
+    x = np.linspace(0, 1, dim)[:, None]
+    mu = rng.uniform(0.1, 2.0, (1, k))
+    A = np.asfortranarray(np.exp(-mu * x) * np.sin(3 * mu * x + 1) + 1e-3 * rng.standard_normal((dim, k)))
+    sp = NumpyVectorSpace(dim)
+    out = dict(A=A)
+    for tag, kw in (('l2', dict(rtol=1e-6)), ('sup', dict(error_norm='sup', rtol=1e-6)),
+                    ('max8', dict(max_interpolation_dofs=8)), ('nodal', dict(rtol=1e-4, nodal_basis=True))):
+        dofs, basis, data = ei_greedy(sp.from_numpy(A.copy()), **kw)
+        out[f'ei_{tag}_dofs'], out[f'ei_{tag}_basis'] = dofs, basis.to_numpy()
+        out[f'ei_{tag}_errors'], out[f'ei_{tag}_coefficients'] = np.array(data['errors']), data['coefficients']
+        out[f'ei_{tag}_matrix'] = data['interpolation_matrix']
+    w = rng.uniform(0.5, 1.5, dim)
+    out['w'] = w
+    for tag, prod in (('euclid', None), ('diag', NumpyMatrixOperator(sps.diags(w).tocsr()))):
+        dofs, basis, data = deim(sp.from_numpy(A.copy()), modes=9, product=prod)
+        out[f'deim_{tag}_dofs'], out[f'deim_{tag}_basis'], out[f'deim_{tag}_svals'] = dofs, basis.to_numpy(), data['svals']
+    dofs, basis, data = deim(sp.from_numpy(A[:, :6].copy()), pod=False)
+    out['deim_nopod_dofs'], out['deim_nopod_basis'] = dofs, basis.to_numpy()
+    np.savez_compressed(OUT / 'ei.npz', **out)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -253,5 +282,6 @@ if __name__ == '__main__':
     thermalblock()
     chol_qr()
     hapod()
+    ei()
     for f in sorted(OUT.glob('*.npz')):
         print(f.name, f.stat().st_size)

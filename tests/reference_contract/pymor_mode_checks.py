@@ -186,3 +186,26 @@ def test_reductor_workflow_next_row_N4():
     assert err < 5e-2 and abs(err - ref_err) < 1e-8        # same ROM error as the all-NumPy pipeline
     # reduced operator matrices agree up to the sign/rotation freedom of the bases: compare outputs instead
     np.testing.assert_allclose(U_rec.to_numpy(), rb_n.lincomb(u_n.to_numpy()).to_numpy(), atol=1e-8)
+
+
+def test_empirical_interpolation_next_row_N5():
+    """pyMOR's own ei_greedy / deim on device arrays: same interpolation DOFs, same collateral bases."""
+    from pymor.algorithms.ei import deim, ei_greedy
+    rng = np.random.default_rng(11)
+    dim, k = 211, 30
+    x = np.linspace(0, 1, dim)[:, None]
+    mu = rng.uniform(0.1, 2.0, (1, k))
+    A = np.asfortranarray(np.exp(-mu * x) * np.sin(3 * mu * x + 1) + 1e-3 * rng.standard_normal((dim, k)))
+    nsp, csp = NumpyVectorSpace(dim), CudaVectorSpace(dim, device=DEVICE)
+    for kw in (dict(rtol=1e-6), dict(error_norm='sup', rtol=1e-6), dict(rtol=1e-4, nodal_basis=True)):
+        dn, bn, datan = ei_greedy(nsp.from_numpy(A.copy()), **kw)
+        dc, bc, datac = ei_greedy(csp.from_numpy(A), **kw)
+        assert isinstance(bc, CudaVectorArray)
+        np.testing.assert_array_equal(dn, dc)
+        np.testing.assert_allclose(bc.to_numpy(), bn.to_numpy(), atol=1e-9)
+        np.testing.assert_allclose(datac['interpolation_matrix'], datan['interpolation_matrix'], atol=1e-9)
+    w = rng.uniform(0.5, 1.5, dim)
+    dn, bn, datan = deim(nsp.from_numpy(A.copy()), modes=9, product=NumpyMatrixOperator(sps.diags(w).tocsr()))
+    dc, bc, datac = deim(csp.from_numpy(A), modes=9, product=CudaDiagonalOperator(w, csp))
+    np.testing.assert_array_equal(dn, dc)
+    np.testing.assert_allclose(datac['svals'], datan['svals'], rtol=1e-10)

@@ -59,7 +59,8 @@ pyst._other_vector_space_types = ['cuda']
 import pytest  # noqa: E402
 
 DEFAULT = ['src/pymortests/vectorarray.py', 'src/pymortests/algorithms/gram_schmidt.py',
-           'src/pymortests/algorithms/svd_va.py', 'src/pymortests/algorithms/pod.py']
+           'src/pymortests/algorithms/svd_va.py', 'src/pymortests/algorithms/pod.py',
+           'src/pymortests/algorithms/chol_qr.py', 'src/pymortests/algorithms/basic.py']
 import os  # noqa: E402
 
 os.chdir(REF)

@@ -522,3 +522,33 @@ def test_next_rows_hapod_and_range_finder(loaded_lib, rng):
     assert O.orthogonality_error(Qh) < 1e-10
     resid = L - Qh @ (Qh.T @ L)
     assert np.linalg.norm(resid) < 1e-8 * np.linalg.norm(L)
+
+
+def test_next_row_empirical_interpolation_golden(loaded_lib):
+    """N5 on the device: EI-greedy and DEIM (amax / dofs / per-column axpy / norm / lincomb kernels) reproduce
+    the reference's interpolation DOFs exactly and its collateral bases to 1e-9."""
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaDiagonalOperator
+    g = load_golden('ei')
+    A = g['A']
+    sp = space_of(A.shape[0])
+    for tag, kw in (('l2', dict(rtol=1e-6)), ('sup', dict(error_norm='sup', rtol=1e-6)),
+                    ('max8', dict(max_interpolation_dofs=8)), ('nodal', dict(rtol=1e-4, nodal_basis=True))):
+        V = sp.from_numpy(A)
+        dofs, basis, data = alg.ei_greedy(V, **kw)
+        np.testing.assert_array_equal(dofs, g[f'ei_{tag}_dofs'])                      # index work: exact
+        np.testing.assert_allclose(basis.to_numpy(), g[f'ei_{tag}_basis'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(data['errors'], g[f'ei_{tag}_errors'], rtol=1e-9)
+        np.testing.assert_allclose(data['interpolation_matrix'], g[f'ei_{tag}_matrix'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(V.lincomb(data['coefficients']).to_numpy(), basis.to_numpy(), atol=1e-7)
+        np.testing.assert_array_equal(V.to_numpy(), A)                                 # copy=True: input untouched
+    for tag, prod in (('euclid', None), ('diag', CudaDiagonalOperator(g['w'], sp))):
+        dofs, basis, data = alg.deim(sp.from_numpy(A), modes=9, product=prod)
+        np.testing.assert_array_equal(dofs, g[f'deim_{tag}_dofs'])
+        np.testing.assert_allclose(data['svals'], g[f'deim_{tag}_svals'], rtol=1e-10)
+        B = basis.to_numpy()
+        signs = np.sign(np.sum(B * g[f'deim_{tag}_basis'], axis=0))
+        np.testing.assert_allclose(B * signs, g[f'deim_{tag}_basis'], rtol=0, atol=1e-8)
+    dofs, basis, _ = alg.deim(sp.from_numpy(A[:, :6]), pod=False)
+    np.testing.assert_array_equal(dofs, g['deim_nopod_dofs'])
+    np.testing.assert_array_equal(basis.to_numpy(), g['deim_nopod_basis'])

@@ -181,3 +181,26 @@ def test_shifted_chol_qr_golden():
     Q1, R1 = O.shifted_chol_qr(np.hstack([Q0, g['A_mild'][:, 5:]]), offset=5, return_R=True)
     np.testing.assert_allclose(Q1, g['Q_offset'], atol=1e-12)
     np.testing.assert_allclose(R1, g['R_offset'], atol=1e-13)
+
+
+def test_empirical_interpolation_golden():
+    """"Next" row N5: EI-greedy and DEIM restatements against the reference's results."""
+    g = load_golden('ei')
+    A = g['A']
+    for tag, kw in (('l2', dict(rtol=1e-6)), ('sup', dict(error_norm='sup', rtol=1e-6)),
+                    ('max8', dict(max_interpolation_dofs=8)), ('nodal', dict(rtol=1e-4, nodal_basis=True))):
+        dofs, basis, data = O.ei_greedy(A, **kw)
+        np.testing.assert_array_equal(dofs, g[f'ei_{tag}_dofs'])
+        np.testing.assert_allclose(basis, g[f'ei_{tag}_basis'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(data['errors'], g[f'ei_{tag}_errors'], rtol=1e-9)
+        np.testing.assert_allclose(data['coefficients'], g[f'ei_{tag}_coefficients'], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(data['interpolation_matrix'], g[f'ei_{tag}_matrix'], rtol=0, atol=1e-9)
+    for tag, w in (('euclid', None), ('diag', g['w'])):
+        dofs, basis, data = O.deim(A, w, modes=9)
+        np.testing.assert_array_equal(dofs, g[f'deim_{tag}_dofs'])
+        np.testing.assert_allclose(data['svals'], g[f'deim_{tag}_svals'], rtol=1e-10)
+        signs = np.sign(np.sum(basis * g[f'deim_{tag}_basis'], axis=0))
+        np.testing.assert_allclose(basis * signs, g[f'deim_{tag}_basis'], rtol=0, atol=1e-8)
+    dofs, basis, _ = O.deim(A[:, :6], use_pod=False)
+    np.testing.assert_array_equal(dofs, g['deim_nopod_dofs'])
+    np.testing.assert_array_equal(basis, g['deim_nopod_basis'])
