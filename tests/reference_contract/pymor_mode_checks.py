@@ -186,6 +186,20 @@ def test_reductor_workflow_next_row_N4():
     assert err < 5e-2 and abs(err - ref_err) < 1e-8        # same ROM error as the all-NumPy pipeline
     # reduced operator matrices agree up to the sign/rotation freedom of the bases: compare outputs instead
     np.testing.assert_allclose(U_rec.to_numpy(), rb_n.lincomb(u_n.to_numpy()).to_numpy(), atol=1e-8)
+    # a17: ProjectionBasedReductor.extend_basis (reductors/basic.py:125-149, :578-603) on the device basis --
+    # append + gram_schmidt(offset=...) resp. POD of the projection error + the orthonormality check
+    red_n = StationaryRBReductor(fom, rb_n, product=fom.h1_0_semi_product)
+    for method in ('gram_schmidt', 'pod'):
+        mu_new = problem.parameter_space.sample_randomly(1)[0]
+        U_new = fom.solve(mu_new)
+        red_n.extend_basis(U_new, method=method)
+        red_c.extend_basis(csp.from_numpy(U_new.to_numpy()), method=method)
+        assert len(red_c.bases['RB']) == len(red_n.bases['RB']) and isinstance(red_c.bases['RB'], CudaVectorArray)
+        Bc, Bn = red_c.bases['RB'].to_numpy(), red_n.bases['RB'].to_numpy()
+        np.testing.assert_allclose(np.abs(np.sum(Bc[:, -1] * Bn[:, -1])) / np.sum(Bn[:, -1] ** 2), 1.0, atol=1e-6)
+        u_c2 = red_c.reduce().solve(mu_new)
+        rec = red_c.reconstruct(u_c2).to_numpy()
+        assert np.linalg.norm(rec - U_new.to_numpy()) / np.linalg.norm(U_new.to_numpy()) < 1e-6   # snapshot is in the basis
 
 
 def test_empirical_interpolation_next_row_N5():
