@@ -119,6 +119,28 @@ int pmc_axpy(pmc_ctx *ctx, double *Y, int64_t csY, const double *X, int64_t csX,
 int pmc_axpy_dot(pmc_ctx *ctx, double *Y, const double *X, const double *alpha, const double *Q,
                  int64_t n, const double *w, double *out, uint32_t flags);
 
+/* One whole Gram-Schmidt sweep in one launch (persistent cooperative kernel, csrc/mgs.cu):
+ *   for j in 0..nq-1:  r[j] = sum_d Q[d + j*csQ] * w[d] * v[d]  (summed over all ranks);  v -= r[j] * Q[:, j]
+ *   norm2 = sum_d w[d] * v[d]^2  (summed over all ranks)
+ * out (nq + 2 doubles, device-accessible, e.g. pinned host memory) receives r[0..nq-1], norm2 and a status
+ * word (0 = ok, 1 = a wait inside the kernel timed out).  Replaces the inner loop of gram_schmidt
+ * (algorithms/gram_schmidt.py:84-93: pairwise_inner + axpy per pair, then norm) and, on row-sharded arrays,
+ * the Gather + host sum per pair of vectorarrays/mpi.py:394-416: after pmc_peer_connect the cross-GPU sum of
+ * every coefficient happens inside the kernel over NVLink peer memory; all ranks must call it with the same
+ * nq in the same order and get bitwise identical r / norm2.  Vectors must be 16-byte aligned, csQ even. */
+int pmc_mgs_sweep(pmc_ctx *ctx, const double *Q, int64_t csQ, int32_t nq, double *v, int64_t n,
+                  const double *w, double *out, uint32_t flags);
+
+/* Peer inboxes for the in-kernel cross-GPU sums of pmc_mgs_sweep (one process per GPU, one box).
+ * pmc_peer_create allocates this rank's inbox and returns its CUDA IPC handle (PMC_IPC_HANDLE_BYTES bytes);
+ * the caller exchanges the handles of all ranks (any transport; pymor_b200 uses torch.distributed's
+ * all_gather_object) and passes them, concatenated in rank order, to pmc_peer_connect. */
+#define PMC_MAX_PEERS 8
+#define PMC_IPC_HANDLE_BYTES 64
+int pmc_peer_create(pmc_ctx *ctx, int rank, int size, void *ipc_handle_out);
+int pmc_peer_connect(pmc_ctx *ctx, const void *handles);
+int pmc_peer_destroy(pmc_ctx *ctx);
+
 /* scal: Y[:, c] *= alpha[c or 0].  Replaces NumpyVectorArrayImpl.scal (numpy.py:85-100). */
 int pmc_scal(pmc_ctx *ctx, double *Y, int64_t csY, int32_t k, int64_t n, const double *alpha,
              int32_t n_alpha, uint32_t flags);

@@ -18,6 +18,8 @@ PMC_ERR_WORKSPACE = -3
 PMC_SYNC = 1
 PMC_SYMMETRIC = 2
 PMC_FORCE_SIMPLE = 4
+PMC_MAX_PEERS = 8
+PMC_IPC_HANDLE_BYTES = 64
 
 LIB_PATH = Path(__file__).resolve().parent / 'lib' / 'libpymor_b200.so'
 
@@ -43,6 +45,10 @@ _CTX_FUNCS = {
     'pmc_measure_fp64_peak': [c_int, c_double, _P],
     'pmc_host_register': [_P, c_size_t, ctypes.POINTER(_P)],
     'pmc_host_unregister': [_P],
+    'pmc_mgs_sweep': [_P, _I64, _I32, _P, _I64, _P, _P, _U32],
+    'pmc_peer_create': [c_int, c_int, _P],
+    'pmc_peer_connect': [_P],
+    'pmc_peer_destroy': [],
     'pmc_ctx_set_option': [ctypes.c_char_p, c_int],
     'pmc_ctx_get_option': [ctypes.c_char_p, ctypes.POINTER(c_int)],
 }
@@ -124,6 +130,7 @@ class DeviceContext:
         self.uploads = []                              # impls whose host -> device copy is still in flight
         self._copy_stream = None
         self.pending = None
+        self._peer_comm = None
         self.fuse_axpy = os.environ.get('PMC_NO_FUSE_AXPY', '0') != '1'
         self.scalar = np.zeros(1)                      # staging for scalar coefficients (read at launch)
         self.scalar_ptr = self.scalar.ctypes.data
@@ -218,6 +225,23 @@ class DeviceContext:
 
     def unregister_host(self, host_ptr):
         self.lib.pmc_host_unregister(self.handle, host_ptr)
+
+    def ensure_peers(self, comm):
+        """Open the peer inboxes of all ranks of ``comm`` (one process per GPU on one box) so that
+        pmc_mgs_sweep can sum its coefficients across the GPUs inside the kernel.  Collective."""
+        if self._peer_comm is not None:
+            if self._peer_comm != comm:
+                raise PmcError('peer inboxes are already connected to a different process group')
+            return
+        if comm.size > PMC_MAX_PEERS:
+            raise PmcError(f'in-kernel sums support at most {PMC_MAX_PEERS} ranks')
+        handle = ctypes.create_string_buffer(PMC_IPC_HANDLE_BYTES)
+        self.call('pmc_peer_create', comm.rank, comm.size, ctypes.cast(handle, _P))
+        blobs = comm.allgather_object(handle.raw)
+        table = ctypes.create_string_buffer(b''.join(blobs), PMC_IPC_HANDLE_BYTES * comm.size)
+        self.call('pmc_peer_connect', ctypes.cast(table, _P))
+        comm.barrier()                 # nobody posts before everybody has connected
+        self._peer_comm = comm
 
     def set_option(self, name, value):
         """Kernel tuning switch (``gram_opts``, ``gram_waves``, ``csr_variant``, ``l2_keep``)."""

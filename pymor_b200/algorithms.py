@@ -22,6 +22,7 @@ touch raw data, like their reference counterparts):
 from __future__ import annotations
 
 import logging
+import os
 
 import numpy as np
 import scipy.linalg as spla
@@ -33,15 +34,41 @@ class AccuracyError(Exception):
     """Raised when the result of :func:`gram_schmidt` fails the orthonormality check."""
 
 
+def _sweep_weight(A, product):
+    """Device address of the diagonal weight (0: Euclidean) if the inner loop of :func:`gram_schmidt` can
+    run as one fused device sweep per pass (``CudaVectorArrayImpl.mgs_sweep``), else ``None``: a real,
+    non-view CudaVectorArray and no product or a diagonal one."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    from pymor_b200.vectorarray import CudaVectorArray, CudaVectorArrayImpl
+    if not isinstance(A, CudaVectorArray) or type(A.impl) is not CudaVectorArrayImpl or A.ind is not None:
+        return None
+    if A.space.comm.size > 8:
+        return None
+    if product is None:
+        return 0
+    if isinstance(product, CudaDiagonalOperator) and product.source == A.space:
+        return product._w.data_ptr()
+    return None
+
+
 def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset=0,
-                 reiterate=True, reiteration_threshold=9e-1, check=True, check_tol=1e-3, copy=True):
+                 reiterate=True, reiteration_threshold=9e-1, check=True, check_tol=1e-3, copy=True, sweep=None):
     """Modified Gram-Schmidt with re-iteration; vectors that are (numerically) zero or linearly
-    dependent are removed.  Returns ``Q`` or ``(Q, R)``."""
+    dependent are removed.  Returns ``Q`` or ``(Q, R)``.
+
+    ``sweep`` (not in the reference; default: environment ``PMC_MGS_SWEEP=1``, else off): run each pass of
+    the inner loop -- all projections of vector i onto the previous vectors and the norm that follows -- as
+    ONE persistent device kernel (``pmc_mgs_sweep``) instead of one launch and one host synchronisation per
+    pair; on row-sharded arrays the per-pair sums over the GPUs happen inside that kernel over NVLink.
+    Same recurrences in the same order; sums are grouped differently, so results agree to rounding."""
     if copy:
         A = A.copy()
     k = len(A)
     R = np.eye(k)
     dropped = []
+    if sweep is None:
+        sweep = os.environ.get('PMC_MGS_SWEEP', '0') == '1'
+    weight_ptr = _sweep_weight(A, product) if sweep else None
     for i in range(offset, k):
         v = A[i]
         norm0 = v.norm(product)[0]
@@ -55,16 +82,32 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
             continue
         cur = norm0
         while True:
-            for j in range(i):
-                if j in dropped:
-                    continue
-                q = A[j]
-                p = q.pairwise_inner(v, product)[0]
-                v.axpy(-p, q)
-                if np.iscomplexobj(p) and not np.iscomplexobj(R):
-                    R = R.astype(np.complex128)
-                R[j, i] += p
-            prev, cur = cur, v.norm(product)[0]
+            if weight_ptr is not None:
+                # fused pass: the kept columns before i are final and orthonormal, column i is swept against
+                # them -- one launch per run of consecutive kept columns (a single one unless vectors were removed)
+                kept = [j for j in range(i) if j not in dropped]
+                runs = []
+                for j in kept:
+                    if runs and runs[-1][0] + runs[-1][1] == j:
+                        runs[-1][1] += 1
+                    else:
+                        runs.append([j, 1])
+                nrm2 = None
+                for start, count in runs or [[0, 0]]:
+                    coeffs, nrm2 = A.impl.mgs_sweep(count, i, weight_ptr, start=start)
+                    R[start:start + count, i] += coeffs
+                prev, cur = cur, float(np.sqrt(nrm2))
+            else:
+                for j in range(i):
+                    if j in dropped:
+                        continue
+                    q = A[j]
+                    p = q.pairwise_inner(v, product)[0]
+                    v.axpy(-p, q)
+                    if np.iscomplexobj(p) and not np.iscomplexobj(R):
+                        R = R.astype(np.complex128)
+                    R[j, i] += p
+                prev, cur = cur, v.norm(product)[0]
             if cur <= rtol * norm0:
                 logger.info('Removing linearly dependent vector %d', i)
                 dropped.append(i)

@@ -17,7 +17,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / 'csrc'
 LIB_DIR = PKG_DIR / 'lib'
 LIB_PATH = LIB_DIR / 'libpymor_b200.so'
-SOURCES = ['ctx.cu', 'blas1.cu', 'gram.cu', 'gram2.cu', 'lincomb.cu', 'csr.cu', 'peak.cu']
+SOURCES = ['ctx.cu', 'blas1.cu', 'mgs.cu', 'gram.cu', 'gram2.cu', 'lincomb.cu', 'csr.cu', 'peak.cu']
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17', '-lineinfo',

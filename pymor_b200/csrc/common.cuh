@@ -29,6 +29,13 @@ struct pmc_ctx {
     int gram_waves;          // target number of CTA waves of the split-n Gram kernel (env PMC_GRAM_WAVES)
     int gram_opts;           // ablation switches for gram_dmma_kernel (env PMC_GRAM_OPTS)
     int l2_keep;             // keep single hot vectors L2-resident (env PMC_NO_L2_KEEP=1 disables)
+    // Gram-Schmidt sweep kernel (mgs.cu): flagged CTA packets, abort flag, step counter; peer inboxes
+    uint64_t *sweep_box;
+    unsigned int *sweep_abort;
+    uint32_t sweep_seq;
+    int peer_rank, peer_size, peer_pending_size;
+    uint64_t *peer_inbox_local;
+    uint64_t *peer_inbox[PMC_MAX_PEERS];
 };
 
 void pmc_set_error(const char *fmt, ...);

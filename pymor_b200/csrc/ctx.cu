@@ -74,6 +74,8 @@ extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
 extern "C" int pmc_ctx_destroy(pmc_ctx *ctx) {
     if (!ctx) return PMC_OK;
     cudaSetDevice(ctx->device);
+    pmc_peer_destroy(ctx);
+    cudaFree(ctx->sweep_box);
     cudaFree(ctx->tickets);
     cudaFree(ctx->partials);
     delete ctx;

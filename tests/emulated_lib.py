@@ -148,6 +148,31 @@ class EmulatedLib:
         _vec(out, 1)[0] = np.sum((_vec(Q, n) if Q else y) * b)
         return PMC_OK
 
+    def pmc_mgs_sweep(self, ctx, Q, csQ, nq, v, n, w, out, flags):
+        """One launch on the device; across ranks the kernel sums over NVLink peer memory -- emulated by the
+        ``sweep_allreduce`` hook the multi-process tests install (sum of a double over the ranks)."""
+        self._note('pmc_mgs_sweep')
+        red = getattr(self, 'sweep_allreduce', None) or (lambda x: x)
+        y = _vec(v, n)
+        ww = _vec(w, n) if w else None
+        o = _vec(out, nq + 2)
+        for j in range(nq):
+            q = _col(Q, csQ, j, n)
+            o[j] = red(float(np.sum(q * (y * ww if w else y))))
+            y -= o[j] * q
+        o[nq] = red(float(np.sum(y * (y * ww if w else y))))
+        o[nq + 1] = 0.0
+        return PMC_OK
+
+    def pmc_peer_create(self, ctx, rank, size, handle_out):
+        return PMC_OK
+
+    def pmc_peer_connect(self, ctx, handles):
+        return PMC_OK
+
+    def pmc_peer_destroy(self, ctx):
+        return PMC_OK
+
     def pmc_scal(self, ctx, Y, csY, k, n, alpha, n_alpha, flags):
         self._note('pmc_scal')
         al = _vec(alpha, n_alpha)

@@ -5,6 +5,7 @@ backend (pymor_b200/dist.py) -- with the C ABI served by the NumPy emulation.  R
 with the oracle evaluated on the global data, and with the oracle's restatement of the reference's
 gather-and-sum (src/pymor/vectorarrays/mpi.py:394-445).
 """
+import os
 import sys
 from pathlib import Path
 
@@ -28,8 +29,6 @@ from pymor_b200.vectorarray import CudaVectorSpace  # noqa: E402
 def main():
     real = '--real' in sys.argv          # real kernels + NCCL, one GPU per rank (tests/test_gpu_multi.py)
     if real:
-        import os
-
         import torch
         local = int(os.environ.get('LOCAL_RANK', '0'))
         torch.cuda.set_device(local)
@@ -39,7 +38,15 @@ def main():
     else:
         device = 'cpu'
         dist.init_process_group('gloo')
-        _lib.set_library_for_testing(EmulatedLib())
+        emu = EmulatedLib()
+
+        def _sum_over_ranks(x):            # what pmc_mgs_sweep does over NVLink peer memory on the GPUs
+            import torch
+            t = torch.tensor([x], dtype=torch.float64)
+            dist.all_reduce(t)
+            return float(t[0])
+        emu.sweep_allreduce = _sum_over_ranks
+        _lib.set_library_for_testing(emu)
     comm = ProcessGroupComm()
     rank, size = comm.rank, comm.size
     for dim in (1, 5, 103) + ((40013,) if real else ()):    # dim < size: some ranks own zero rows
@@ -91,6 +98,12 @@ def main():
             Qo, Ro = O.gram_schmidt(A, w, return_R=True)
             np.testing.assert_allclose(R, Ro, atol=1e-11)
             np.testing.assert_allclose(Q.to_numpy(), Qo, atol=1e-11)
+            # one fused sweep per pass, the sums over the ranks inside the kernel (peer inboxes); on the GPUs
+            # only on request until the kernel has been seen green there (tools/gpu_session_r2_first.sh)
+            if not real or os.environ.get('PMC_TEST_SWEEP') == '1':
+                Qs, Rs = alg.gram_schmidt(VA, product=prod, return_R=True, sweep=True)
+                np.testing.assert_allclose(Rs, Ro, atol=1e-11)
+                np.testing.assert_allclose(Qs.to_numpy(), Qo, atol=1e-11)
             U, s = alg.pod(VA, product=prod, method='method_of_snapshots')
             Uo, so = O.pod(A, w)
             np.testing.assert_allclose(s, so, rtol=1e-10)

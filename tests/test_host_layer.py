@@ -511,3 +511,43 @@ def test_standalone_empirical_interpolation_golden(emu):
     dofs, basis, _ = alg.deim(sp.from_numpy(A[:, :6]), pod=False)
     np.testing.assert_array_equal(dofs, g['deim_nopod_dofs'])
     np.testing.assert_array_equal(basis.to_numpy(), g['deim_nopod_basis'])
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
+def test_standalone_gram_schmidt_fused_sweep(emu, name):
+    """gram_schmidt(sweep=True): every pass of the inner loop is ONE pmc_mgs_sweep call (plus norm / scal per
+    vector); products without a device weight vector fall back to the pair-by-pair loop.  Same Q, R."""
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('gram_schmidt')
+    sp = space_of(g['A'].shape[0])
+    prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp),
+            'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
+    VA = sp.from_numpy(g['A'])
+    emu.calls.clear()
+    Q, R = alg.gram_schmidt(VA, product=prod, return_R=True, sweep=True)
+    np.testing.assert_array_equal(VA.to_numpy(), g['A'])
+    np.testing.assert_allclose(Q.to_numpy(), g[f'Q_{name}'], atol=1e-11)
+    np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
+    k = g['A'].shape[1]
+    if name == 'csr':
+        assert 'pmc_mgs_sweep' not in emu.calls
+    else:
+        assert k - 1 <= emu.calls.count('pmc_mgs_sweep') <= 4 * (k - 1)      # about one per pass, not one per pair
+        assert 'pmc_axpy_dot' not in emu.calls and 'pmc_axpy' not in emu.calls
+        assert emu.calls.count('pmc_pairwise_inner') == 0
+    # views, removal of dependent vectors and the offset form keep working (fallbacks inside)
+    A = g['A'].copy()
+    A[:, 3] = A[:, 1] - 2 * A[:, 2]
+    Qd, Rd = alg.gram_schmidt(sp.from_numpy(A), product=prod, return_R=True, sweep=True)
+    Qo, Ro = O.gram_schmidt(A, None if name == 'euclid' else (g['w'] if name == 'diag' else csr_from(g, 'M')), return_R=True)
+    assert len(Qd) == Qo.shape[1] < A.shape[1]
+    np.testing.assert_allclose(Qd.to_numpy(), Qo, atol=1e-9)
+    np.testing.assert_allclose(Rd, Ro, atol=1e-9)
+    if name == 'euclid':
+        Q0 = alg.gram_schmidt(sp.from_numpy(g['A'][:, :4]), sweep=True)
+        Q0.append(sp.from_numpy(g['A'][:, 10:]))
+        Q1 = alg.gram_schmidt(Q0, offset=4, copy=False, sweep=True)
+        np.testing.assert_allclose(Q1.to_numpy(), g['Q_offset'], atol=1e-11)
+        V = sp.from_numpy(g['A'])
+        Qv = alg.gram_schmidt(V[2:9], sweep=True)                       # a view: pair-by-pair path
+        np.testing.assert_allclose(Qv.to_numpy(), O.gram_schmidt(g['A'][:, 2:9]), atol=1e-11)

@@ -24,6 +24,17 @@ if grep -q "pytest gram2 exit 0" gpurun_out/r02_pytest_gram2.log; then
         > gpurun_out/r02_ncu_gram2.log 2>&1
 fi
 unset PMC_TEST_GRAM2
+# fused Gram-Schmidt sweep (csrc/mgs.cu): gated parity test under a short timeout (the kernel's waits give up
+# after 5 s on their own), then config 3 pair-by-pair vs swept
+PMC_TEST_SWEEP=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 --timeout-method thread \
+    -k mgs_sweep > gpurun_out/r02_pytest_sweep.log 2>&1
+echo "pytest sweep exit $?" >> gpurun_out/r02_pytest_sweep.log
+tail -n 4 gpurun_out/r02_pytest_sweep.log
+if grep -q "pytest sweep exit 0" gpurun_out/r02_pytest_sweep.log; then
+    timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 > gpurun_out/r02_gs_10Mx256_pairs.log 2>&1
+    timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --sweep > gpurun_out/r02_gs_10Mx256_sweep.log 2>&1
+    grep -hE '^\{' gpurun_out/r02_gs_10Mx256_pairs.log gpurun_out/r02_gs_10Mx256_sweep.log | cut -c1-500
+fi
 # HBM-bound kernels: 10M-DOF vectors, 12 columns -> a few hundred launches; capture a handful of each kind
 timeout 300 python tools/bench_gs.py --dofs 10000000 --k 12 > gpurun_out/r02_gs_10Mx12.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'reduce_cols|axpy_dot|elementwise' \

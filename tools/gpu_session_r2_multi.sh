@@ -1,0 +1,18 @@
+#!/bin/bash
+# Multi-GPU session of round 2 (start with `gpurun --gpus 2`, repeat with --gpus 8 once green):
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_session_r2_multi.sh'
+# The fused Gram-Schmidt sweep sums its coefficients across the GPUs inside the kernel (peer inboxes over
+# NVLink); its waits give up after 5 s, every command runs under `timeout`.
+set -u
+mkdir -p gpurun_out
+N=$(nvidia-smi -L | wc -l)
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+PMC_TEST_SWEEP=1 timeout 600 $TR tests/sharded_worker.py --real > gpurun_out/r02_sharded_worker_${N}gpu.log 2>&1
+echo "exit $?" >> gpurun_out/r02_sharded_worker_${N}gpu.log
+tail -n 5 gpurun_out/r02_sharded_worker_${N}gpu.log
+timeout 600 $TR tools/bench_gs.py --dofs 10000000 --k 256 > gpurun_out/r02_gs_${N}gpu_pairs.log 2>&1
+if grep -q "exit 0" gpurun_out/r02_sharded_worker_${N}gpu.log; then
+    timeout 600 $TR tools/bench_gs.py --dofs 10000000 --k 256 --sweep > gpurun_out/r02_gs_${N}gpu_sweep.log 2>&1
+fi
+timeout 1200 $TR bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r02_bench_${N}gpu.log 2>&1
+grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_pairs.log gpurun_out/r02_gs_${N}gpu_sweep.log gpurun_out/r02_bench_${N}gpu.log | cut -c1-600
