@@ -309,6 +309,20 @@ def test_reference_contract_suite_on_cuda_backend():
 
 @pytest.mark.reference
 @pytest.mark.skipif(not HAVE_REFERENCE, reason='reference not present')
+def test_reference_operator_contract_on_cuda_operators():
+    """pymortests/operators/operators.py (apply, apply2, pairwise_apply2, apply_adjoint, H, assemble, jacobian,
+    as_range_array, restricted, inverse wrappers, arithmetic) and pymortests/algorithms/projection.py (project with
+    and without products, to sub-bases) with CudaDiagonalOperator / CudaCsrOperator / a LincombOperator of them
+    registered as the fixture generators -- the Operator half of the plug-in boundary."""
+    import re
+    r = _run('run_operator_contract.py')
+    tail = r.stdout[-3000:]
+    assert r.returncode == 0, tail
+    assert ' passed' in tail and not re.search(r'\d+ (failed|error)', tail)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REFERENCE, reason='reference not present')
 def test_pymor_algorithms_run_unchanged():
     r = _run('run_contract.py', str(ROOT / 'tests' / 'reference_contract' / 'pymor_mode_checks.py'))
     tail = r.stdout[-3000:]
