@@ -223,3 +223,64 @@ def test_empirical_interpolation_next_row_N5():
     dc, bc, datac = deim(csp.from_numpy(A), modes=9, product=CudaDiagonalOperator(w, csp))
     np.testing.assert_array_equal(dn, dc)
     np.testing.assert_allclose(datac['svals'], datan['svals'], rtol=1e-10)
+
+
+def test_reference_stored_golden_vector_thermalblock_pod():
+    """The reference's OWN golden vector for this path: pymortests/testdata/check_results/
+    test_thermalblock_results/c8a460e4... = results of `pymordemos/thermalblock.py --alg=pod 2 2 3 5`
+    (test_thermalblock_results, pymortests/demos.py:386-402): 81 FEM snapshots (20 201 DOFs), POD with the
+    H1_0-semi product, 5 modes, coercive RB reductor, errors of the ROM at 10 random parameters.  The demo
+    module itself needs cyclopts/matplotlib (absent), so its `reduce_pod` pipeline (thermalblock.py:362-393) is
+    re-driven here; with pyMOR's NumPy backend that reproduces the stored numbers to 1e-12, which validates the
+    re-drive.  Then the POD is swapped for (a) the CPU oracle and (b) pyMOR's `pod` on device arrays with the
+    CUDA product operator: the downstream ROM errors must still match the stored golden vector."""
+    import pickle
+
+    from oracle import numpy_path as O
+    from pymor.algorithms.error import reduction_error_analysis
+    from pymor.analyticalproblems.thermalblock import thermal_block_problem
+    from pymor.discretizers.builtin import discretize_stationary_cg
+    from pymor.parameters.functionals import ExpressionParameterFunctional
+    from pymor.reductors.coercive import CoerciveRBReductor
+    from pymor.tools.random import new_rng
+    golden_file = ('/root/reference/src/pymortests/testdata/check_results/test_thermalblock_results/'
+                   'c8a460e412d9170f12508ab3608fd7e1e1750603')
+    with open(golden_file, 'rb') as f:
+        assert f.readline().decode().strip() == "['--alg=pod', 2, 2, 3, 5]"
+        gold = pickle.load(f)
+
+    problem = thermal_block_problem(num_blocks=(2, 2))
+    fom, _ = discretize_stationary_cg(problem, diameter=1. / 100)
+    space = fom.parameters.space(0.1, 1.)
+    coercivity = ExpressionParameterFunctional('min(diffusion)', fom.parameters)
+    snaps = fom.operator.source.empty()
+    for mu in space.sample_uniformly(3):
+        snaps.append(fom.solve(mu))
+    prod = fom.h1_0_semi_product
+    P = prod.matrix.tocsr()
+    csp = CudaVectorSpace(fom.solution_space.dim, device=DEVICE)
+
+    def pod_numpy():
+        return pod(snaps, modes=5, product=prod)[0]
+
+    def pod_oracle():
+        U, _ = O.pod(snaps.to_numpy(), P, modes=5, method='qr_svd')
+        return fom.solution_space.from_numpy(U)
+
+    def pod_device():
+        U, _ = pod(csp.from_numpy(snaps.to_numpy()), modes=5, product=CudaCsrOperator(P, csp))
+        assert isinstance(U, CudaVectorArray)
+        return fom.solution_space.from_numpy(U.to_numpy())
+
+    for name, make_basis, tol in (('numpy', pod_numpy, 1e-11), ('oracle', pod_oracle, 1e-8), ('device', pod_device, 1e-8)):
+        red = CoerciveRBReductor(fom, product=prod, coercivity_estimator=coercivity, check_orthonormality=False)
+        red.extend_basis(make_basis(), method='trivial')
+        rom = red.reduce()
+        with new_rng(42):                     # the test parameters of the stored run (pyMOR's default seed)
+            res = reduction_error_analysis(rom, fom=fom, reductor=red, error_estimator=True,
+                                           error_norms=(fom.h1_0_semi_norm, fom.l2_norm), condition=True,
+                                           test_mus=space.sample_randomly(10), basis_sizes=1)
+        assert list(np.asarray(res['basis_sizes'])) == list(gold['basis_sizes']), name
+        np.testing.assert_allclose(res['norms'], gold['norms'], rtol=1e-11, err_msg=name)
+        for key in ('errors', 'max_errors', 'rel_errors', 'max_rel_errors', 'error_estimates'):
+            np.testing.assert_allclose(res[key], gold[key], rtol=tol, err_msg=f'{name}: {key}')
