@@ -338,11 +338,15 @@ def shifted_chol_qr(A, W=None, return_R=False, maxiter=3, offset=0, product_norm
 # empirical interpolation ("next" row N5; src/pymor/algorithms/ei.py)
 # ------------------------------------------------------------------------------------------------
 def ei_greedy(U, error_norm=None, atol=None, rtol=None, max_interpolation_dofs=None, nodal_basis=False):
-    """EI-greedy (ei.py:30-179) on a (dim, len) matrix; ``error_norm`` None (Euclidean) or 'sup'.
+    """EI-greedy (ei.py:30-179) on a (dim, len) matrix; ``error_norm`` None (Euclidean), 'sup' or a
+    callable ``(dim, len) matrix -> (len,) norms`` (e.g. ``lambda E: norm(E, W)`` for a product norm).
     Returns interpolation DOFs, collateral basis (dim, m) and the data dict of the reference."""
     U = np.array(U, order='F', dtype=float)
     k = U.shape[1]
-    measure = (lambda E: np.max(np.abs(E), axis=0)) if error_norm == 'sup' else (lambda E: norm(E))
+    if callable(error_norm):
+        measure = error_norm
+    else:
+        measure = (lambda E: np.max(np.abs(E), axis=0)) if error_norm == 'sup' else (lambda E: norm(E))
     picked, basis = [], np.zeros((U.shape[0], 0), order='F')
     K, coefficients = np.eye(k), np.zeros((k, 0))
     max_errs = []

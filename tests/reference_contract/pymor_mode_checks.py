@@ -284,3 +284,48 @@ def test_reference_stored_golden_vector_thermalblock_pod():
         np.testing.assert_allclose(res['norms'], gold['norms'], rtol=1e-11, err_msg=name)
         for key in ('errors', 'max_errors', 'rel_errors', 'max_rel_errors', 'error_estimates'):
             np.testing.assert_allclose(res[key], gold[key], rtol=tol, err_msg=f'{name}: {key}')
+
+
+def test_reference_stored_golden_vector_burgers_ei_greedy():
+    """The reference's stored golden vector for the empirical-interpolation row (N5):
+    pymortests/testdata/check_results/test_burgers_ei_results/* = `pymordemos/burgers_ei.py 1 2 2 5 2 5
+    --grid=20` (test_burgers_ei_results, pymortests/demos.py:405-413): EI-greedy errors and triangularity errors
+    for 202 operator evaluations of the FV Burgers model with the L2-product norm, 5 interpolation DOFs.  The
+    demo module needs cyclopts/matplotlib, so `interpolate_operators`' evaluation loop (algorithms/ei.py:404-417)
+    is re-driven; with pyMOR's NumPy backend that reproduces the stored numbers, then EI-greedy is swapped for
+    the CPU oracle and for pyMOR's `ei_greedy` on device arrays with the CUDA diagonal product."""
+    import glob
+    import math
+    import pickle
+
+    from oracle import numpy_path as O
+    from pymor.algorithms.ei import ei_greedy
+    from pymor.analyticalproblems.burgers import burgers_problem_2d
+    from pymor.discretizers.builtin import RectGrid, discretize_instationary_fv
+    gold = None
+    for fn in glob.glob('/root/reference/src/pymortests/testdata/check_results/test_burgers_ei_results/*'):
+        with open(fn, 'rb') as f:
+            if f.readline().decode().strip() == "['1', '2', '2', '5', '2', '5', '--grid=20']":
+                gold = pickle.load(f)
+    assert gold is not None
+    problem = burgers_problem_2d(vx=1., vy=1., initial_data_type='sin', parameter_range=(1, 2), torus=True)
+    fom, _ = discretize_instationary_fv(problem, diameter=1. / (20 / math.sqrt(2)), grid_type=RectGrid,
+                                        num_flux='engquist_osher', lxf_lambda=1., nt=100)
+    ev = fom.operator.range.empty()
+    for mu in problem.parameter_space.sample_uniformly(2):
+        ev.append(fom.operator.apply(fom.solve(mu), mu=mu))
+    w = np.asarray(fom.l2_product.matrix.diagonal(), dtype=float)
+    assert (fom.l2_product.matrix - sps.diags(w)).tocsr().nnz == 0       # the FV L2 product is diagonal
+    E = ev.to_numpy()
+    csp = CudaVectorSpace(ev.dim, device=DEVICE)
+    cprod = CudaDiagonalOperator(w, csp)
+    runs = {
+        'numpy': lambda: ei_greedy(ev.copy(), error_norm=fom.l2_norm, max_interpolation_dofs=5)[2],
+        'oracle': lambda: O.ei_greedy(E, error_norm=lambda M: O.norm(M, w), max_interpolation_dofs=5)[2],
+        'device': lambda: ei_greedy(csp.from_numpy(E), error_norm=lambda U: U.norm(cprod), max_interpolation_dofs=5)[2],
+    }
+    for name, run in runs.items():
+        data = run()
+        np.testing.assert_allclose(data['errors'], gold['errors'], rtol=1e-12 if name == 'numpy' else 1e-9, err_msg=name)
+        np.testing.assert_allclose(data['triangularity_errors'], gold['triangularity_errors'], rtol=0, atol=1e-14,
+                                   err_msg=name)
