@@ -127,9 +127,12 @@ int pmc_axpy_dot(pmc_ctx *ctx, double *Y, const double *X, const double *alpha, 
  * (algorithms/gram_schmidt.py:84-93: pairwise_inner + axpy per pair, then norm) and, on row-sharded arrays,
  * the Gather + host sum per pair of vectorarrays/mpi.py:394-416: after pmc_peer_connect the cross-GPU sum of
  * every coefficient happens inside the kernel over NVLink peer memory; all ranks must call it with the same
- * nq in the same order and get bitwise identical r / norm2.  Vectors must be 16-byte aligned, csQ even. */
-int pmc_mgs_sweep(pmc_ctx *ctx, const double *Q, int64_t csQ, int32_t nq, double *v, int64_t n,
-                  const double *w, double *out, uint32_t flags);
+ * nq in the same order and get bitwise identical r / norm2.  Vectors must be 16-byte aligned, csQ even.
+ * Z (optional, needs w): panel of the pre-weighted columns Z[:, j] = w * Q[:, j] (pmc_diag_apply, once per
+ * column when it becomes final); the dots then read Z[:, j] instead of Q[:, j] and w, which takes the weight
+ * stream out of every step (r[j] = sum_d Z[d + j*csZ] * v[d]). */
+int pmc_mgs_sweep(pmc_ctx *ctx, const double *Q, int64_t csQ, const double *Z, int64_t csZ, int32_t nq,
+                  double *v, int64_t n, const double *w, double *out, uint32_t flags);
 
 /* Peer inboxes for the in-kernel cross-GPU sums of pmc_mgs_sweep (one process per GPU, one box).
  * pmc_peer_create allocates this rank's inbox and returns its CUDA IPC handle (PMC_IPC_HANDLE_BYTES bytes);

@@ -45,7 +45,7 @@ _CTX_FUNCS = {
     'pmc_measure_fp64_peak': [c_int, c_double, _P],
     'pmc_host_register': [_P, c_size_t, ctypes.POINTER(_P)],
     'pmc_host_unregister': [_P],
-    'pmc_mgs_sweep': [_P, _I64, _I32, _P, _I64, _P, _P, _U32],
+    'pmc_mgs_sweep': [_P, _I64, _P, _I64, _I32, _P, _I64, _P, _P, _U32],
     'pmc_peer_create': [c_int, c_int, _P],
     'pmc_peer_connect': [_P],
     'pmc_peer_destroy': [],

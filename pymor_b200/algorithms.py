@@ -69,6 +69,21 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
     if sweep is None:
         sweep = os.environ.get('PMC_MGS_SWEEP', '0') == '1'
     weight_ptr = _sweep_weight(A, product) if sweep else None
+    Z = None                # weighted sweeps: panel of the pre-weighted final columns w * q_j (same positions as in A)
+    if weight_ptr:
+        from pymor_b200.vectorarray import CudaVectorArrayImpl
+        try:
+            Z = CudaVectorArrayImpl.allocate(A.space, k)
+        except RuntimeError:                       # no room for a second panel: the sweeps stream w instead
+            Z = None
+
+    def weigh(first, count):
+        # Z[:, first:first+count] = w * A[:, first:first+count] for columns that have become final
+        if Z is not None and count and A.impl.n:
+            A.space.ctx.flush()
+            A.space.ctx.call('pmc_diag_apply', weight_ptr, A.impl._ptr(first), A.impl.ld, Z._ptr(first), Z.ld, count,
+                             A.impl.n, 0)
+    weigh(0, offset)
     for i in range(offset, k):
         v = A[i]
         norm0 = v.norm(product)[0]
@@ -79,6 +94,7 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
         if i == 0:
             v.scal(1 / norm0)
             R[0, 0] = norm0
+            weigh(0, 1)
             continue
         cur = norm0
         while True:
@@ -94,7 +110,7 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
                         runs.append([j, 1])
                 nrm2 = None
                 for start, count in runs or [[0, 0]]:
-                    coeffs, nrm2 = A.impl.mgs_sweep(count, i, weight_ptr, start=start)
+                    coeffs, nrm2 = A.impl.mgs_sweep(count, i, weight_ptr, start=start, weighted=Z)
                     R[start:start + count, i] += coeffs
                 prev, cur = cur, float(np.sqrt(nrm2))
             else:
@@ -117,6 +133,7 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
                 continue
             v.scal(1 / cur)
             R[i, i] = cur
+            weigh(i, 1)
             break
     if dropped:
         del A[dropped]

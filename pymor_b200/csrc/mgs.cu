@@ -11,7 +11,8 @@
 //
 //   * every CTA owns a fixed set of rows, so the update of v needs no synchronisation at all; the
 //     deferred update  v -= r[j-1] q_{j-1}  is merged into the pass that accumulates <q_j, v>  (one pass
-//     over q_{j-1}, q_j, w from HBM and v from L2 per step);
+//     over q_{j-1}, q_j, w from HBM and v from L2 per step; with a pre-weighted panel z_j = w * q_j, kept
+//     by the caller next to Q, the dots read z_j and the w stream disappears: two HBM streams per step);
 //   * the only grid-wide exchange per step is the sum of the CTA partials.  Each CTA posts its partial
 //     as a flagged packet (two 8-byte words, each carrying 32 value bits and the 32-bit step number, so
 //     a reader never sees a torn value and no fence or atomic is needed) and every CTA polls all packets:
@@ -42,6 +43,8 @@ struct SweepParams {
     const double *Q;
     int64_t csQ;
     int nq;
+    const double *Z;            // optional pre-weighted panel z_j = w * q_j (then the dot needs no w stream)
+    int64_t csZ;
     double *v;
     const double *w;
     int64_t n;
@@ -153,8 +156,12 @@ __device__ __forceinline__ double sweep_pass(double *__restrict__ v, const doubl
     return s;
 }
 
-template <bool WEIGHTED>
+// WMODE 0: Euclidean; 1: diagonal weight applied in every pass (q_{j-1}, q_j, w stream from HBM);
+// 2: pre-weighted panel Z (z_j = w * q_j, written once when q_j became final): the dots read z_j instead of
+// q_j and no w -- two HBM streams per step instead of three; only the closing norm pass reads w.
+template <int WMODE>
 __global__ void __launch_bounds__(S_TPB, 1) mgs_sweep_kernel(const SweepParams p) {
+    constexpr bool W_DOT = WMODE == 1, W_NORM = WMODE != 0;
     __shared__ double wsum[S_TPB / 32];
     __shared__ double s_coeff;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,15 +172,16 @@ __global__ void __launch_bounds__(S_TPB, 1) mgs_sweep_kernel(const SweepParams p
     double coeff = 0.0;                       // r[j-1]: the update still owed to v
     for (int j = 0; j <= p.nq; ++j) {
         const double *x = p.Q + (int64_t)(j - 1) * p.csQ;      // q_{j-1} (unused for j == 0)
-        const double *q = p.Q + (int64_t)j * p.csQ;            // q_j     (unused for j == nq)
+        // dot operand of step j: q_j, or z_j = w * q_j from the pre-weighted panel (unused for j == nq)
+        const double *q = (WMODE == 2) ? p.Z + (int64_t)j * p.csZ : p.Q + (int64_t)j * p.csQ;
         double s;
         if (j == 0) {
-            s = (p.nq == 0) ? sweep_pass<false, true, WEIGHTED>(p.v, x, 0.0, q, p.w, p.n, pol_v, pol_w, pol_q)
-                            : sweep_pass<false, false, WEIGHTED>(p.v, x, 0.0, q, p.w, p.n, pol_v, pol_w, pol_q);
+            s = (p.nq == 0) ? sweep_pass<false, true, W_NORM>(p.v, x, 0.0, q, p.w, p.n, pol_v, pol_w, pol_q)
+                            : sweep_pass<false, false, W_DOT>(p.v, x, 0.0, q, p.w, p.n, pol_v, pol_w, pol_q);
         } else if (j < p.nq) {
-            s = sweep_pass<true, false, WEIGHTED>(p.v, x, -coeff, q, p.w, p.n, pol_v, pol_w, pol_q);
+            s = sweep_pass<true, false, W_DOT>(p.v, x, -coeff, q, p.w, p.n, pol_v, pol_w, pol_q);
         } else {
-            s = sweep_pass<true, true, WEIGHTED>(p.v, x, -coeff, q, p.w, p.n, pol_v, pol_w, pol_q);
+            s = sweep_pass<true, true, W_NORM>(p.v, x, -coeff, q, p.w, p.n, pol_v, pol_w, pol_q);
         }
         // CTA partial
         s = warp_sum(s);
@@ -229,19 +237,21 @@ int ensure_sweep_state(pmc_ctx *ctx) {
 
 }  // namespace
 
-extern "C" int pmc_mgs_sweep(pmc_ctx *ctx, const double *Q, int64_t csQ, int32_t nq, double *v, int64_t n,
-                             const double *w, double *out, uint32_t flags) {
+extern "C" int pmc_mgs_sweep(pmc_ctx *ctx, const double *Q, int64_t csQ, const double *Z, int64_t csZ, int32_t nq,
+                             double *v, int64_t n, const double *w, double *out, uint32_t flags) {
     PMC_REQUIRE(ctx && nq >= 0 && n >= 0 && out, "bad arguments");
     PMC_REQUIRE(n == 0 || v, "NULL vector");
     PMC_REQUIRE(nq == 0 || n == 0 || Q, "NULL panel");
     PMC_REQUIRE(aligned16(v) && aligned16(Q) && aligned16(w) && (csQ % 2) == 0,
                 "pmc_mgs_sweep needs 16-byte aligned vectors and an even column stride");
     PMC_REQUIRE(csQ > 0 || nq <= 1, "pmc_mgs_sweep needs a positive column stride");
+    PMC_REQUIRE(!Z || (w && aligned16(Z) && (csZ % 2) == 0 && (csZ > 0 || nq <= 1)),
+                "a pre-weighted panel needs the weight vector, 16-byte alignment and an even positive stride");
     int rc = ensure_sweep_state(ctx);
     if (rc) return rc;
     SweepParams p;
     memset(&p, 0, sizeof(p));
-    p.Q = Q; p.csQ = csQ; p.nq = nq; p.v = v; p.w = w; p.n = n; p.out = out;
+    p.Q = Q; p.csQ = csQ; p.Z = Z; p.csZ = csZ; p.nq = nq; p.v = v; p.w = w; p.n = n; p.out = out;
     p.cta_box = ctx->sweep_box;
     p.abort_flag = ctx->sweep_abort;
     p.seq_base = ctx->sweep_seq;
@@ -255,10 +265,9 @@ extern "C" int pmc_mgs_sweep(pmc_ctx *ctx, const double *Q, int64_t csQ, int32_t
     void *args[] = {&p};
     const dim3 grid(ctx->sm_count), block(S_TPB);
     // cooperative launch: all CTAs are guaranteed to be co-resident (they wait for each other)
-    if (w)
-        PMC_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)mgs_sweep_kernel<true>, grid, block, args, 0, ctx->stream));
-    else
-        PMC_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)mgs_sweep_kernel<false>, grid, block, args, 0, ctx->stream));
+    const void *kernel = !w ? (const void *)mgs_sweep_kernel<0>
+                         : Z ? (const void *)mgs_sweep_kernel<2> : (const void *)mgs_sweep_kernel<1>;
+    PMC_CHECK_CUDA(cudaLaunchCooperativeKernel(kernel, grid, block, args, 0, ctx->stream));
     return pmc_after_launch(ctx, 1, flags);
 }
 

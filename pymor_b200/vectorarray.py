@@ -509,19 +509,21 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         del keep_a
         return sp.reduction_result(out, ka)
 
-    def mgs_sweep(self, nq, col, weight_ptr=0, start=0):
+    def mgs_sweep(self, nq, col, weight_ptr=0, start=0, weighted=None):
         """Orthogonalise column ``col`` against columns ``start .. start+nq-1`` (orthonormal) in ONE launch:
         the inner loop of gram_schmidt (gram_schmidt.py:84-93) as a persistent kernel, cross-GPU sums
         included (pmc_mgs_sweep).  Returns the ``nq`` projection coefficients and the squared norm of
-        the updated vector -- on every rank the same bits."""
+        the updated vector -- on every rank the same bits.  ``weighted``: optional impl holding the
+        pre-weighted columns ``w * q_j`` at the same positions (takes the weight stream out of every step)."""
         sp, ctx = self.space, self.space.ctx
         assert 0 <= start and start + nq <= col < self._len
         ctx.flush()
         if sp.comm.size > 1:
             ctx.ensure_peers(sp.comm)
         out = ctx.host_f64(nq + 2)
-        ctx.call('pmc_mgs_sweep', self._ptr(start), self.ld, nq, self._ptr(col), self.n, weight_ptr, out.data_ptr(),
-                 PMC_SYNC)
+        zp, zcs = (weighted._ptr(start), weighted.ld) if weighted is not None and weight_ptr else (0, 0)
+        ctx.call('pmc_mgs_sweep', self._ptr(start), self.ld, zp, zcs, nq, self._ptr(col), self.n, weight_ptr,
+                 out.data_ptr(), PMC_SYNC)
         res = out[:nq + 2].numpy().copy()
         if res[nq + 1] != 0.0:
             raise _lib.PmcError('pmc_mgs_sweep: a wait inside the kernel timed out (ranks out of step?)')

@@ -148,7 +148,7 @@ class EmulatedLib:
         _vec(out, 1)[0] = np.sum((_vec(Q, n) if Q else y) * b)
         return PMC_OK
 
-    def pmc_mgs_sweep(self, ctx, Q, csQ, nq, v, n, w, out, flags):
+    def pmc_mgs_sweep(self, ctx, Q, csQ, Z, csZ, nq, v, n, w, out, flags):
         """One launch on the device; across ranks the kernel sums over NVLink peer memory -- emulated by the
         ``sweep_allreduce`` hook the multi-process tests install (sum of a double over the ranks)."""
         self._note('pmc_mgs_sweep')
@@ -158,7 +158,11 @@ class EmulatedLib:
         o = _vec(out, nq + 2)
         for j in range(nq):
             q = _col(Q, csQ, j, n)
-            o[j] = red(float(np.sum(q * (y * ww if w else y))))
+            if Z:
+                assert w, 'pre-weighted panel without weight vector'
+                o[j] = red(float(np.sum(_col(Z, csZ, j, n) * y)))
+            else:
+                o[j] = red(float(np.sum(q * (y * ww if w else y))))
             y -= o[j] * q
         o[nq] = red(float(np.sum(y * (y * ww if w else y))))
         o[nq + 1] = 0.0

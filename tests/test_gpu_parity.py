@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sps
 
-from conftest import csr_from, load_golden
+from conftest import assert_gram_schmidt_golden, csr_from, load_golden
 from oracle import numpy_path as O
 
 pytestmark = pytest.mark.gpu
@@ -567,11 +567,13 @@ def test_mgs_sweep_parity(loaded_lib, rng):
         Qh = np.linalg.qr(rng.standard_normal((dim, k)))[0]
         w = rng.uniform(0.5, 1.5, dim)
         prod = CudaDiagonalOperator(w, sp)
-        for weighted in (False, True):
+        for mode in ('euclid', 'w-stream', 'pre-weighted'):
+            weighted = mode != 'euclid'
             for nq in sorted({0, min(1, k - 1), k - 1}):
                 A = np.asfortranarray(np.hstack([Qh[:, :k - 1], rng.standard_normal((dim, 1))]))
                 V = sp.from_numpy(A)
-                coeffs, nrm2 = V.impl.mgs_sweep(nq, k - 1, prod._w.data_ptr() if weighted else 0)
+                Z = prod.apply(V).impl if mode == 'pre-weighted' else None       # z_j = w * q_j
+                coeffs, nrm2 = V.impl.mgs_sweep(nq, k - 1, prod._w.data_ptr() if weighted else 0, weighted=Z)
                 v = A[:, -1].copy()
                 want = np.zeros(nq)
                 for j in range(nq):
@@ -586,8 +588,7 @@ def test_mgs_sweep_parity(loaded_lib, rng):
     sp = space_of(g['A'].shape[0])
     for name, prod in (('euclid', None), ('diag', CudaDiagonalOperator(g['w'], sp))):
         Q, R = alg.gram_schmidt(sp.from_numpy(g['A']), product=prod, return_R=True, sweep=True)
-        np.testing.assert_allclose(Q.to_numpy(), g[f'Q_{name}'], atol=1e-11)
-        np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
+        assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, None if prod is None else g['w'])
     n, k = 2_000_000, 24
     sp = space_of(n)
     A = sp.random_device(k, seed=3, scale=1.0 / np.sqrt(n))
