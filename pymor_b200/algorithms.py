@@ -14,7 +14,8 @@ touch raw data, like their reference counterparts):
 * :func:`shifted_chol_qr`       -- src/pymor/algorithms/chol_qr.py:16-252 ("next" row N1: the GEMM-bound
   orthonormalisation -- three Gramians + three block lincombs instead of k^2 dot/axpy pairs with a
   host sync each, i.e. the variant that scales over DOF-sharded GPUs)
-* :func:`inc_vectorarray_hapod` -- src/pymor/algorithms/hapod.py:333 ("next" row N3)
+* :func:`inc_vectorarray_hapod`, :func:`dist_vectorarray_hapod` -- src/pymor/algorithms/hapod.py:333, :372
+  ("next" row N3)
 * :func:`randomized_range_finder` -- src/pymor/algorithms/rand_la.py:20 ("next" row N2, fixed-size mode)
 * :func:`ei_greedy`, :func:`deim` -- src/pymor/algorithms/ei.py:30, :182 ("next" row N5: empirical
   interpolation data; the backend sees ``amax`` / ``dofs`` / per-column ``axpy`` / ``norm`` / ``lincomb``)
@@ -361,6 +362,55 @@ def inc_vectorarray_hapod(steps, U, eps, omega, product=None):
             modes.scal(svals)
             carried = modes
     return modes, svals, snap_count
+
+
+def dist_vectorarray_hapod(num_slices, U, eps, omega, arity=None, product=None):
+    """Distributed hierarchical approximate POD ("next" row N3; reference:
+    src/pymor/algorithms/hapod.py:372-410 over the tree of :106-126 with the local tolerances of :414-424):
+    the snapshots are cut into ``num_slices`` slices, every leaf is the :func:`pod` of one slice, every inner
+    node the :func:`pod` of its children's modes scaled by their singular values; ``arity=None`` gives the
+    two-level tree (one POD per slice, one of the collected modes).  Returns ``modes, svals, snap_count``.
+    The nodes run one after the other on the device (the reference's ``executor`` only adds host threads)."""
+    chunk = -(-len(U) // num_slices)
+    starts = list(range(0, len(U), chunk))
+    fan = len(starts) if arity is None else arity
+
+    def build(slices):                         # nested lists; an int is a leaf (slice number)
+        if len(slices) > fan:
+            return [build(list(part)) if len(part) > 1 else int(part[0]) for part in np.array_split(slices, fan)]
+        return [int(i) for i in slices]
+
+    def depth(node):
+        return 1 if isinstance(node, int) else 1 + max(depth(c) for c in node)
+
+    tree = build(list(range(len(starts))))
+    levels = depth(tree)
+
+    def local_pod(V, snap_count, is_root):
+        if is_root:
+            tol = np.sqrt(snap_count) * omega * eps
+        else:
+            tol = np.sqrt(snap_count) / np.sqrt(levels - 1) * np.sqrt(1 - omega ** 2) * eps
+        return pod(V, product=product, atol=0., rtol=0., l2_err=tol, orth_tol=1e-10 if is_root else np.inf)
+
+    def visit(node, is_root):
+        if isinstance(node, int):
+            V = U[starts[node]:starts[node] + chunk].copy()
+            count = len(V)
+        else:
+            V, count = None, 0
+            for child in node:
+                modes, svals, c = visit(child, False)
+                modes.scal(svals)
+                count += c
+                if V is None:
+                    V = modes
+                else:
+                    V.append(modes, remove_from_other=True)
+        modes, svals = local_pod(V, count, is_root)
+        return modes, svals, count
+
+    return visit(tree, True)
 
 
 def randomized_range_finder(A, basis_size, power_iterations=0, range_product=None, qr_method='gram_schmidt'):

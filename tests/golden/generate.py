@@ -238,6 +238,13 @@ def hapod():
             modes, svals, count = inc_vectorarray_hapod(steps, sp.from_numpy(A.copy()), 1e-3, 0.75, product=prod)
             out[f'modes_{name}_{steps}'], out[f'svals_{name}_{steps}'] = modes.to_numpy(), svals
             assert count == k
+    from pymor.algorithms.hapod import dist_vectorarray_hapod
+    for name, prod in (('euclid', None), ('diag', NumpyMatrixOperator(sps.diags(w).tocsr()))):
+        for slices, arity in ((1, None), (5, None), (7, 2)):
+            modes, svals, count = dist_vectorarray_hapod(slices, sp.from_numpy(A.copy()), 1e-3, 0.75, arity=arity,
+                                                         product=prod)
+            out[f'dist_modes_{name}_{slices}_{arity}'], out[f'dist_svals_{name}_{slices}_{arity}'] = modes.to_numpy(), svals
+            assert count == k
     np.savez_compressed(OUT / 'hapod.npz', **out)
 
 

@@ -509,6 +509,13 @@ def test_next_rows_hapod_and_range_finder(loaded_lib, rng):
         m = min(len(modes), ref_modes.shape[1])
         np.testing.assert_allclose(svals[:m], ref_svals[:m], rtol=1e-7)
         assert O.subspace_angle(ref_modes[:, :7], modes.to_numpy()[:, :7], w) < 1e-6      # the 7 signal modes
+    for slices, arity in ((5, None), (7, 2)):                     # distributed trees (hapod.py:372)
+        modes, svals, count = alg.dist_vectorarray_hapod(slices, sp.from_numpy(A), 1e-3, 0.75, arity=arity, product=prod)
+        ref_modes, ref_svals = g[f'dist_modes_diag_{slices}_{arity}'], g[f'dist_svals_diag_{slices}_{arity}']
+        assert count == A.shape[1] and abs(len(modes) - ref_modes.shape[1]) <= 1
+        m = min(len(modes), ref_modes.shape[1])
+        np.testing.assert_allclose(svals[:m], ref_svals[:m], rtol=1e-7)
+        assert O.subspace_angle(ref_modes[:, :7], modes.to_numpy()[:, :7], w) < 1e-6
     dim = 20011
     L, Rr = rng.standard_normal((dim, 6)), rng.standard_normal((6, 40))
     B = L @ Rr                                                    # rank 6, placed in 40 columns of a sparse dim x dim

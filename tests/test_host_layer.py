@@ -482,6 +482,26 @@ def test_standalone_inc_hapod_golden(emu, name):
         assert O.orthogonality_error(modes.to_numpy(), W) < 1e-10
 
 
+@pytest.mark.parametrize('name', ['euclid', 'diag'])
+def test_standalone_dist_hapod_golden(emu, name):
+    """N3, distributed tree: two-level (one POD per slice + root) and a binary tree over 7 slices."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    g = load_golden('hapod')
+    A, w = g['A'], g['w']
+    sp = space_of(A.shape[0])
+    W = None if name == 'euclid' else w
+    prod = None if name == 'euclid' else CudaDiagonalOperator(w, sp)
+    for slices, arity in ((1, None), (5, None), (7, 2)):
+        V = sp.from_numpy(A)
+        modes, svals, count = alg.dist_vectorarray_hapod(slices, V, 1e-3, 0.75, arity=arity, product=prod)
+        ref_modes, ref_svals = g[f'dist_modes_{name}_{slices}_{arity}'], g[f'dist_svals_{name}_{slices}_{arity}']
+        assert count == A.shape[1] and len(modes) == ref_modes.shape[1]
+        np.testing.assert_allclose(svals, ref_svals, rtol=1e-8)
+        assert O.subspace_angle(ref_modes[:, :7], modes.to_numpy()[:, :7], W) < 1e-6      # the 7 signal modes
+        assert O.orthogonality_error(modes.to_numpy(), W) < 1e-10
+        np.testing.assert_array_equal(V.to_numpy(), A)                                     # input untouched
+
+
 def test_standalone_randomized_range_finder(emu, rng):
     """"Next" row N2: the range of a rank-5 operator is captured by 8 random samples."""
     from pymor_b200.operators import CudaCsrOperator
