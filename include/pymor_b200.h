@@ -199,7 +199,9 @@ int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32
                  uint32_t flags);
 
 /* Roofline denominators measured on the spot: sustained FP64 tensor-core (DMMA) and DFMA
- * throughput in TFLOP/s over `ms` milliseconds of back-to-back issue on every SM. */
+ * throughput in TFLOP/s over `ms` milliseconds of back-to-back issue on every SM.  use_dmma: 0 = DFMA, 1 = DMMA,
+ * 2 = half of the warps DMMA / half DFMA, 3 = every warp interleaves both (2 and 3 report the combined rate: do the
+ * two instruction kinds share the FP64 units?). */
 int pmc_measure_fp64_peak(pmc_ctx *ctx, int use_dmma, double ms, double *tflops_out);
 
 #ifdef __cplusplus

@@ -255,7 +255,7 @@ class DeviceContext:
 
     def measure_fp64_peak(self, use_dmma=True, ms=200.0):
         out = np.zeros(1)
-        self.call('pmc_measure_fp64_peak', int(bool(use_dmma)), float(ms), out.ctypes.data)
+        self.call('pmc_measure_fp64_peak', int(use_dmma), float(ms), out.ctypes.data)   # 0 DFMA, 1 DMMA, 2/3 mixed
         return float(out[0])
 
 

@@ -34,6 +34,32 @@ __global__ void __launch_bounds__(512, 1) dfma_peak_kernel(int iters, double *si
     if (s == 123.456) sink[0] = s;
 }
 
+// Are the DMMA and the DFMA datapath the same FP64 units?  Mixed issue: mode 2 = half of the warps of every SMSP
+// run the DMMA loop, the other half the DFMA loop; mode 3 = every warp interleaves 16 DMMA with 16 DFMA.
+// If the combined rate exceeds the larger single rate, a hybrid tile kernel could use both.
+__global__ void __launch_bounds__(512, 1) mixed_peak_kernel(int iters, int interleave, double *sink) {
+    double c[16][2], d[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; d[i] = threadIdx.x * 1e-3 + i; }
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9, e = 1e-12;
+    const bool do_mma = interleave || (((threadIdx.x >> 5) >> 2) & 1) == 0;   // warps 0-3, 8-11: one pair per SMSP
+    const bool do_fma = interleave || !do_mma;
+    for (int it = 0; it < iters; ++it) {
+        if (do_mma) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+        }
+        if (do_fma) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = fma(d[i], a, e);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1] + d[i];
+    if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace
 
 extern "C" int pmc_measure_fp64_peak(pmc_ctx *ctx, int use_dmma, double ms, double *tflops_out) {
@@ -48,14 +74,17 @@ extern "C" int pmc_measure_fp64_peak(pmc_ctx *ctx, int use_dmma, double ms, doub
     // calibrate so that one launch runs for about `ms`, then take the best of 3 launches
     for (int round = 0; round < 5; ++round) {
         PMC_CHECK_CUDA(cudaEventRecord(e0, ctx->stream));
-        if (use_dmma) dmma_peak_kernel<<<grid, threads, 0, ctx->stream>>>(iters, ctx->partials);
+        if (use_dmma >= 2) mixed_peak_kernel<<<grid, threads, 0, ctx->stream>>>(iters, use_dmma == 3, ctx->partials);
+        else if (use_dmma) dmma_peak_kernel<<<grid, threads, 0, ctx->stream>>>(iters, ctx->partials);
         else dfma_peak_kernel<<<grid, threads, 0, ctx->stream>>>(iters, ctx->partials);
         PMC_CHECK_CUDA(cudaEventRecord(e1, ctx->stream));
         PMC_CHECK_CUDA(cudaEventSynchronize(e1));
         PMC_CHECK_CUDA(cudaEventElapsedTime(&t, e0, e1));
         ctx->launches += 1;
-        const double flop_per_iter = use_dmma ? 16.0 * 512.0 /*8x8x4 FMA*/ * (threads / 32)
-                                              : 16.0 * 2.0 * threads;
+        const double mma_flop = 16.0 * 512.0 /*8x8x4 FMA*/ * (threads / 32), fma_flop = 16.0 * 2.0 * threads;
+        const double flop_per_iter = use_dmma == 3 ? mma_flop + fma_flop           // every warp does both
+                                     : use_dmma == 2 ? 0.5 * (mma_flop + fma_flop)  // half the warps each
+                                     : use_dmma ? mma_flop : fma_flop;
         const double tf = flop_per_iter * iters * grid / (t * 1e-3) * 1e-12;
         if (round >= 2 && tf > best) best = tf;
         if (round < 2) {

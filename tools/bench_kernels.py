@@ -44,6 +44,9 @@ def main():
         ctx = sp.ctx
         if peak is None:
             peak = ctx.measure_fp64_peak(True, 200.0)
+            print(json.dumps({'fp64_peaks_tflops': {'dmma': peak, 'dfma': ctx.measure_fp64_peak(0, 100.0),
+                                                    'mixed_by_warp': ctx.measure_fp64_peak(2, 100.0),
+                                                    'mixed_interleaved': ctx.measure_fp64_peak(3, 100.0)}}), flush=True)
         A = sp.random_device(k, seed=1, scale=1.0 / np.sqrt(n))
         w = torch.rand(n, device='cuda', dtype=torch.float64) + 0.5
         out = torch.empty(k * k, device='cuda', dtype=torch.float64)
