@@ -85,6 +85,19 @@ def test_gram_parity(loaded_lib, rng, dim, ka, kb, weighted):
 # round-1 GPU budget was spent: its index maps are CPU-checked (tests/test_gram2_model.py) but it has not
 # run on a B200 yet, so this test only runs on request (PMC_TEST_GRAM2=1, tools/gpu_session_r2_gram2.sh)
 # until it has been seen green once -- then drop the gate and, if the A/B favours it, make it the default.
+def _block_error_map(G, G_ref, scale):
+    """Max scaled error per 32x32 block (the unit a warp of the tile kernels owns) -- printed when a Gram parity
+    assertion fails, so that one GPU session is enough to tell WHICH block / tile kind is wrong."""
+    err = np.abs(G - G_ref) / scale
+    nb_i, nb_j = -(-G.shape[0] // 32), -(-G.shape[1] // 32)
+    m = np.zeros((nb_i, nb_j))
+    for bi in range(nb_i):
+        for bj in range(nb_j):
+            m[bi, bj] = np.nanmax(np.nan_to_num(err[32 * bi:32 * bi + 32, 32 * bj:32 * bj + 32], nan=np.inf))
+    with np.printoptions(precision=1, linewidth=250, threshold=100000):
+        return f'max scaled error per 32x32 block (rows = block row i, 4 blocks = one 128 tile):\n{m}'
+
+
 @pytest.mark.skipif(os.environ.get('PMC_TEST_GRAM2') != '1', reason='gram2 kernel awaits its first GPU session')
 @pytest.mark.parametrize('opts', [16, 16 | 32, 16 | 64, 16 | 128, 16 | 32 | 64 | 128])
 def test_gram2_variant_parity(loaded_lib, rng, opts):
@@ -103,8 +116,12 @@ def test_gram2_variant_parity(loaded_lib, rng, opts):
                 G0, S0 = VA.inner(VB, prod), VA.gramian(prod)
                 ctx.set_option('gram_opts', opts)
                 G, S = VA.inner(VB, prod), VA.gramian(prod)
-                assert O.gram_rel_error(G, O.inner(A, B, wv), A, B, wv) < GRAM_TOL
-                assert O.gram_rel_error(S, O.gramian(A, wv), A, A, wv) < GRAM_TOL
+                tag = f'dim={dim} ka={ka} kb={kb} weighted={wv is not None} opts={opts}'
+                na, nb = O.norm(A, wv), O.norm(B, wv)
+                assert O.gram_rel_error(G, O.inner(A, B, wv), A, B, wv) < GRAM_TOL, \
+                    f'general product, {tag}\n' + _block_error_map(G, O.inner(A, B, wv), np.outer(na, nb))
+                assert O.gram_rel_error(S, O.gramian(A, wv), A, A, wv) < GRAM_TOL, \
+                    f'SYRK, {tag}\n' + _block_error_map(S, O.gramian(A, wv), np.outer(na, na))
                 np.testing.assert_array_equal(S, S.T)
                 np.testing.assert_array_equal(S, VA.gramian(prod))
                 # same products, same order inside a split: the general product is bitwise the first kernel's;
