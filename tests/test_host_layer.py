@@ -588,3 +588,30 @@ def test_standalone_gram_schmidt_fused_sweep(emu, name):
         V = sp.from_numpy(g['A'])
         Qv = alg.gram_schmidt(V[2:9], sweep=True)                       # a view: pair-by-pair path
         np.testing.assert_allclose(Qv.to_numpy(), O.gram_schmidt(g['A'][:, 2:9]), atol=1e-11)
+
+
+def test_fused_sweep_randomised(emu, rng):
+    """Swept and pair-by-pair Gram-Schmidt take the same decisions (removed vectors, re-iterations) on random
+    inputs with zero, dependent and strongly overlapping columns; A = Q R and orthonormality hold for both."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    for _ in range(150):
+        dim = int(rng.integers(1, 40))
+        k = int(rng.integers(1, min(dim, 12) + 1))
+        A = rng.standard_normal((dim, k))
+        for _ in range(int(rng.integers(0, 3))):
+            j, kind = int(rng.integers(0, k)), int(rng.integers(0, 3))
+            if kind == 0:
+                A[:, j] = 0
+            elif kind == 1 and j > 0:
+                A[:, j] = A[:, :j] @ rng.standard_normal(j)
+            else:
+                A[:, j] += 5 * A[:, 0]
+        sp = space_of(dim)
+        prod = CudaDiagonalOperator(rng.uniform(0.5, 1.5, dim), sp) if rng.integers(0, 2) else None
+        Q0, R0 = alg.gram_schmidt(sp.from_numpy(A), product=prod, return_R=True, sweep=False)
+        Q1, R1 = alg.gram_schmidt(sp.from_numpy(A), product=prod, return_R=True, sweep=True)
+        assert len(Q0) == len(Q1)
+        np.testing.assert_allclose(Q1.to_numpy() @ R1, A, atol=1e-11)
+        np.testing.assert_allclose(Q0.to_numpy() @ R0, A, atol=1e-11)
+        if len(Q1):
+            assert np.abs(Q1.gramian(prod) - np.eye(len(Q1))).max() < 1e-13
