@@ -26,3 +26,43 @@ def test_flop_model():
     n, k = 10_000_000, 1000
     assert bench.pod_flops(n, k, k) == n * k * (k + 1) + 2 * n * k * k + n * k * (k + 1)
     assert abs(bench.pod_flops(n, k, k) / 4.0e13 - 1) < 0.01          # ~4.0e13 flop
+
+
+def test_ctypes_tables_match_the_header():
+    """Every prototype of include/pymor_b200.h is bound in pymor_b200/_lib.py with the same number of arguments and
+    matching pointer / integer kinds (an ABI drift between the header and the ctypes tables would corrupt the call
+    stack silently)."""
+    import ctypes
+    import re
+
+    from pymor_b200 import _lib
+    text = (ROOT / 'include' / 'pymor_b200.h').read_text()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = re.findall(r'^(?:int|size_t|int64_t|const char \*)\s*(pmc_\w+)\s*\(([^;]*?)\)\s*;', text, flags=re.M | re.S)
+    assert len(protos) == len(_lib.EXPORTED_SYMBOLS)
+
+    def kind(decl):
+        decl = decl.strip()
+        if decl == 'void' or not decl:
+            return None
+        if '*' in decl:
+            return 'ptr'
+        if decl.startswith('double'):
+            return 'double'
+        return 'int'
+
+    def ckind(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type(ctypes.POINTER(ctypes.c_int))) and \
+                issubclass(t, ctypes._Pointer):
+            return 'ptr'
+        if t is ctypes.c_double:
+            return 'double'
+        return 'int'
+
+    for name, args in protos:
+        want = [k for k in (kind(a) for a in args.split(',')) if k]
+        if name in _lib._CTX_FUNCS:
+            have = ['ptr'] + [ckind(t) for t in _lib._CTX_FUNCS[name]]
+        else:
+            have = [ckind(t) for t in _lib._OTHER_FUNCS[name][0]]
+        assert have == want, (name, have, want)
