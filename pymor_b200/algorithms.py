@@ -53,7 +53,8 @@ def _sweep_weight(A, product):
 
 
 def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset=0,
-                 reiterate=True, reiteration_threshold=9e-1, check=True, check_tol=1e-3, copy=True, sweep=None):
+                 reiterate=True, reiteration_threshold=9e-1, check=True, check_tol=1e-3, copy=True, sweep=None,
+                 variant='mgs'):
     """Modified Gram-Schmidt with re-iteration; vectors that are (numerically) zero or linearly
     dependent are removed.  Returns ``Q`` or ``(Q, R)``.
 
@@ -61,7 +62,16 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
     the inner loop -- all projections of vector i onto the previous vectors and the norm that follows -- as
     ONE persistent device kernel (``pmc_mgs_sweep``) instead of one launch and one host synchronisation per
     pair; on row-sharded arrays the per-pair sums over the GPUs happen inside that kernel over NVLink.
-    Same recurrences in the same order; sums are grouped differently, so results agree to rounding."""
+    Same recurrences in the same order; sums are grouped differently, so results agree to rounding.
+
+    ``variant`` (not in the reference): ``'mgs'`` is the reference's modified Gram-Schmidt.  ``'cgs2'`` projects
+    against ALL previous vectors at once per pass -- ``r = Q^T W v`` (one streaming launch, one host sync),
+    ``v -= Q r`` (one block lincomb + axpy) -- with the same norm-drop re-iteration rule ("twice is enough"):
+    the QR factorisation it converges to is the same (it is unique), the HBM traffic per pass is the same as
+    MGS's (Q is read twice), but a pass costs two host synchronisations instead of one per previous vector,
+    which is what makes the orthonormalisation scale over row-sharded GPUs.  Uses only the VectorArray
+    interface (``inner``, ``lincomb``, ``axpy``), so it also runs on pyMOR's own array classes."""
+    assert variant in ('mgs', 'cgs2')
     if copy:
         A = A.copy()
     k = len(A)
@@ -99,7 +109,23 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
             continue
         cur = norm0
         while True:
-            if weight_ptr is not None:
+            if variant == 'cgs2':
+                # classical pass against all kept previous vectors at once (runs of consecutive columns are views)
+                kept = [j for j in range(i) if j not in dropped]
+                runs = []
+                for j in kept:
+                    if runs and runs[-1][0] + runs[-1][1] == j:
+                        runs[-1][1] += 1
+                    else:
+                        runs.append([j, 1])
+                coeffs = [A[start:start + count].inner(v, product)[:, 0] for start, count in runs]
+                for (start, count), r in zip(runs, coeffs):
+                    if np.iscomplexobj(r) and not np.iscomplexobj(R):
+                        R = R.astype(np.complex128)
+                    v.axpy(-1., A[start:start + count].lincomb(r))
+                    R[start:start + count, i] += r
+                prev, cur = cur, v.norm(product)[0]
+            elif weight_ptr is not None:
                 # fused pass: the kept columns before i are final and orthonormal, column i is swept against
                 # them -- one launch per run of consecutive kept columns (a single one unless vectors were removed)
                 kept = [j for j in range(i) if j not in dropped]

@@ -122,7 +122,10 @@ int launch_reduce(pmc_ctx *ctx, const double *A, int64_t csA, const double *B, i
         const double *a = A + (int64_t)c0 * csA;
         const double *b = NORM ? nullptr : B + (int64_t)c0 * csB;
         bool vec = vec_ok(a, csA) && (NORM || vec_ok(b, csB)) && vec_ok(w, 0);
-        const int keep = (ctx->l2_keep && k == 1 && n * 8 <= L2_KEEP_BYTES) ? 1 : 0;
+        // one hot vector: a single pair (k == 1), or one column broadcast against a wide panel (csB == 0: the
+        // block projection r = Q^T W v of classical Gram-Schmidt) -- the panel streams past it evict_first
+        const bool one_hot = k == 1 || (!NORM && csB == 0 && csA != 0);
+        const int keep = (ctx->l2_keep && one_hot && n * 8 <= L2_KEEP_BYTES) ? 1 : 0;
         dim3 grid(bx, kc);
 #define PMC_LAUNCH_RED(WT, VC)                                                                   \
     reduce_cols_kernel<NORM, WT, VC><<<grid, TPB, 0, ctx->stream>>>(a, csA, b, csB, w, n,          \

@@ -104,6 +104,10 @@ def main():
                 Qs, Rs = alg.gram_schmidt(VA, product=prod, return_R=True, sweep=True)
                 np.testing.assert_allclose(Rs, Ro, atol=1e-11)
                 np.testing.assert_allclose(Qs.to_numpy(), Qo, atol=1e-11)
+            if not real or os.environ.get('PMC_TEST_SWEEP') == '1':      # (new drivers: on the GPUs on request)
+                Qc, Rc = alg.gram_schmidt(VA, product=prod, return_R=True, variant='cgs2')    # two syncs per pass
+                np.testing.assert_allclose(Rc, Ro, atol=1e-10)
+                np.testing.assert_allclose(Qc.to_numpy(), Qo, atol=1e-10)
             U, s = alg.pod(VA, product=prod, method='method_of_snapshots')
             Uo, so = O.pod(A, w)
             np.testing.assert_allclose(s, so, rtol=1e-10)

@@ -629,3 +629,14 @@ def test_mgs_sweep_parity(loaded_lib, rng):
     D.axpy(-1.0, Qp)
     assert np.max(D.norm(prod)) < 1e-12
     assert fused_launches < 8 * k                      # a handful of launches per vector, not 2 per pair
+    # classical variant with re-orthogonalisation: composed from the streaming inner / block lincomb / axpy kernels
+    Qc, Rc = alg.gram_schmidt(A, product=prod, return_R=True, variant='cgs2')
+    np.testing.assert_allclose(Rc, Rp, rtol=0, atol=1e-11)
+    assert np.max(np.abs(Qc.gramian(prod) - np.eye(k))) < 1e-13
+    D = Qc.copy()
+    D.axpy(-1.0, Qp)
+    assert np.max(D.norm(prod)) < 1e-11
+    for name, gprod in (('euclid', None), ('diag', CudaDiagonalOperator(g['w'], space_of(g['A'].shape[0])))):
+        sp_g = space_of(g['A'].shape[0]) if gprod is None else gprod.source
+        Q, R = alg.gram_schmidt(sp_g.from_numpy(g['A']), product=gprod, return_R=True, variant='cgs2')
+        assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, None if gprod is None else g['w'], tight=1e-11)

@@ -615,3 +615,47 @@ def test_fused_sweep_randomised(emu, rng):
         np.testing.assert_allclose(Q0.to_numpy() @ R0, A, atol=1e-11)
         if len(Q1):
             assert np.abs(Q1.gramian(prod) - np.eye(len(Q1))).max() < 1e-13
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
+def test_standalone_gram_schmidt_cgs2(emu, rng, name):
+    """variant='cgs2': one block projection (streaming inner with a broadcast column) + one block lincomb per pass
+    instead of one dot + axpy per previous vector; converges to the same (unique) QR factorisation."""
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('gram_schmidt')
+    sp = space_of(g['A'].shape[0])
+    prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp),
+            'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
+    W = {'euclid': None, 'diag': g['w'], 'csr': csr_from(g, 'M')}[name]
+    VA = sp.from_numpy(g['A'])
+    emu.calls.clear()
+    Q, R = alg.gram_schmidt(VA, product=prod, return_R=True, variant='cgs2')
+    np.testing.assert_array_equal(VA.to_numpy(), g['A'])
+    assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, W, tight=1e-11)
+    k = g['A'].shape[1]
+    assert emu.calls.count('pmc_lincomb') <= 4 * k and 'pmc_axpy_dot' not in emu.calls     # per pass, not per pair
+    if name == 'euclid':
+        Q0 = alg.gram_schmidt(sp.from_numpy(g['A'][:, :4]), variant='cgs2')
+        Q0.append(sp.from_numpy(g['A'][:, 10:]))
+        Q1 = alg.gram_schmidt(Q0, offset=4, copy=False, variant='cgs2')
+        np.testing.assert_allclose(Q1.to_numpy(), g['Q_offset'], atol=1e-11)
+    for _ in range(60):                                  # random inputs with degeneracies: same decisions as MGS
+        dim = int(rng.integers(1, 40))
+        kk = int(rng.integers(1, min(dim, 12) + 1))
+        A = rng.standard_normal((dim, kk))
+        for _ in range(int(rng.integers(0, 3))):
+            j, kind = int(rng.integers(0, kk)), int(rng.integers(0, 3))
+            if kind == 0:
+                A[:, j] = 0
+            elif kind == 1 and j > 0:
+                A[:, j] = A[:, :j] @ rng.standard_normal(j)
+            else:
+                A[:, j] += 5 * A[:, 0]
+        sp2 = space_of(dim)
+        p2 = None if name == 'euclid' else CudaDiagonalOperator(rng.uniform(0.5, 1.5, dim), sp2)
+        Q0, R0 = alg.gram_schmidt(sp2.from_numpy(A), product=p2, return_R=True)
+        Q1, R1 = alg.gram_schmidt(sp2.from_numpy(A), product=p2, return_R=True, variant='cgs2')
+        assert len(Q0) == len(Q1)
+        np.testing.assert_allclose(Q1.to_numpy() @ R1, A, atol=1e-11)
+        if len(Q1):
+            assert np.abs(Q1.gramian(p2) - np.eye(len(Q1))).max() < 1e-13

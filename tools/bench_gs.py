@@ -27,6 +27,8 @@ def main():
     ap.add_argument('--dofs', dest='n', type=int, default=10_000_000)
     ap.add_argument('--k', type=int, default=256)
     ap.add_argument('--cpu-n', type=int, default=0, help='also time the oracle on this many rows')
+    ap.add_argument('--variant', default='mgs', choices=['mgs', 'cgs2'],
+                    help="cgs2: block projection per pass (streaming inner + block lincomb), two host syncs per pass")
     ap.add_argument('--sweep', action='store_true',
                     help='one fused device sweep per pass (pmc_mgs_sweep, in-kernel sums over the GPUs) instead of one '
                          'launch + host sync per pair')
@@ -55,7 +57,8 @@ def main():
     w = torch.rand(space.local_dim, generator=gen, device=space.device, dtype=torch.float64) + 0.5
     prod = CudaDiagonalOperator(w, space)
 
-    counts = {'pairwise_inner': 0, 'axpy': 0, 'scal': 0, 'mgs_sweep': 0}
+    counts = {'pairwise_inner': 0, 'axpy': 0, 'scal': 0, 'mgs_sweep': 0, 'inner': 0, 'lincomb': 0}
+    cgs_cols = [0]
     sweep_pairs = [0]
     for name in counts:
         orig = getattr(CudaVectorArrayImpl, name)
@@ -64,22 +67,29 @@ def main():
             counts[_name] += 1
             if _name == 'mgs_sweep':
                 sweep_pairs[0] += a[0]
+            if _name == 'lincomb':
+                cgs_cols[0] += len(a[0])
             return _orig(self, *a, **kw)
         setattr(CudaVectorArrayImpl, name, wrapped)
 
     # warm up the kernels on a small slice
-    alg.gram_schmidt(A[:8].copy(), product=prod, copy=False, sweep=args.sweep)
+    alg.gram_schmidt(A[:8].copy(), product=prod, copy=False, sweep=args.sweep, variant=args.variant)
     for c in counts:
         counts[c] = 0
     sweep_pairs[0] = 0
+    cgs_cols[0] = 0
     torch.cuda.synchronize()
     l0 = space.ctx.launch_count
     t0 = time.perf_counter()
-    Q, R = alg.gram_schmidt(A, product=prod, return_R=True, copy=False, check=False, sweep=args.sweep)
+    Q, R = alg.gram_schmidt(A, product=prod, return_R=True, copy=False, check=False, sweep=args.sweep,
+                            variant=args.variant)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     launches = space.ctx.launch_count - l0
-    if args.sweep:           # same byte model: every swept pair is a weighted dot + an axpy, every sweep ends in a norm
+    if args.variant == 'cgs2':   # same byte model: projecting onto c columns = c weighted dots + c axpys' worth of traffic
+        pair_steps = cgs_cols[0]
+        norms = counts['pairwise_inner']
+    elif args.sweep:         # same byte model: every swept pair is a weighted dot + an axpy, every sweep ends in a norm
         pair_steps = sweep_pairs[0]
         norms = counts['pairwise_inner'] + counts['mgs_sweep']
     else:
@@ -89,7 +99,7 @@ def main():
     err = float(np.max(np.abs(Q.gramian(prod) - np.eye(len(Q)))))
     peaks = ROOT / 'MEASURED_PEAKS.json'
     hbm = json.loads(peaks.read_text())['hbm_gbs'] if peaks.exists() else 6650.0
-    out = {'workload': f'gram_schmidt {n} x {k}, diag-W, re-iterated', 'fused_sweep': bool(args.sweep), 'n_gpus': world, 'seconds': dt, 'pair_steps': pair_steps,
+    out = {'workload': f'gram_schmidt {n} x {k}, diag-W, re-iterated', 'fused_sweep': bool(args.sweep), 'variant': args.variant, 'n_gpus': world, 'seconds': dt, 'pair_steps': pair_steps,
            'weighted_norms': norms, 'scals': counts['scal'], 'algorithmic_bytes': nbytes,
            'achieved_gbs': nbytes / dt * 1e-9, 'hbm_peak_gbs': hbm,
            'peak_source': 'MEASURED_PEAKS.json' if peaks.exists() else 'fallback 6650 GB/s',

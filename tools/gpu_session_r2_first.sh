@@ -35,6 +35,8 @@ if grep -q "pytest sweep exit 0" gpurun_out/r02_pytest_sweep.log; then
     timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --sweep > gpurun_out/r02_gs_10Mx256_sweep.log 2>&1
     grep -hE '^\{' gpurun_out/r02_gs_10Mx256_pairs.log gpurun_out/r02_gs_10Mx256_sweep.log | cut -c1-500
 fi
+timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --variant cgs2 > gpurun_out/r02_gs_10Mx256_cgs2.log 2>&1
+grep -hE '^\{' gpurun_out/r02_gs_10Mx256_cgs2.log | cut -c1-500
 timeout 300 python tools/bench_cholqr.py --dofs 10000000 --k 256 > gpurun_out/r02_cholqr_10Mx256.log 2>&1
 grep -hE '^\{' gpurun_out/r02_cholqr_10Mx256.log | cut -c1-400
 # HBM-bound kernels: 10M-DOF vectors, 12 columns -> a few hundred launches; capture a handful of each kind
