@@ -329,3 +329,18 @@ def test_reference_stored_golden_vector_burgers_ei_greedy():
         np.testing.assert_allclose(data['errors'], gold['errors'], rtol=1e-12 if name == 'numpy' else 1e-9, err_msg=name)
         np.testing.assert_allclose(data['triangularity_errors'], gold['triangularity_errors'], rtol=0, atol=1e-14,
                                    err_msg=name)
+
+
+@pytest.mark.parametrize('kind', ['euclid', 'diag', 'csr'])
+def test_block_gram_schmidt_variant_vs_pymor_mgs(kind):
+    """`pymor_b200.algorithms.gram_schmidt(variant='cgs2')` is written against the VectorArray interface only: on
+    pyMOR's own NumpyVectorArray and on CudaVectorArray it reproduces pyMOR's (modified) gram_schmidt -- the QR
+    factorisation is unique."""
+    from pymor_b200 import algorithms as alg
+    A, nsp, csp, nprod, cprod = make(157, 12, 1, kind)
+    Qn, Rn = gram_schmidt(nsp.from_numpy(A.copy()), product=nprod, return_R=True)
+    Q1, R1 = alg.gram_schmidt(nsp.from_numpy(A.copy()), product=nprod, return_R=True, variant='cgs2')
+    Q2, R2 = alg.gram_schmidt(csp.from_numpy(A), product=cprod, return_R=True, variant='cgs2')
+    for Q, R in ((Q1, R1), (Q2, R2)):
+        np.testing.assert_allclose(Q.to_numpy(), Qn.to_numpy(), rtol=0, atol=1e-11)
+        np.testing.assert_allclose(R, Rn, rtol=0, atol=1e-11)
