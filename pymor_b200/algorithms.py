@@ -118,7 +118,10 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
                         runs[-1][1] += 1
                     else:
                         runs.append([j, 1])
-                coeffs = [A[start:start + count].inner(v, product)[:, 0] for start, count in runs]
+                # r = Q^T (W v): weigh the single vector once instead of streaming the weight past every column of Q
+                # (this is the reference's own evaluation order of apply2, operators/interface.py:108)
+                wv = v if product is None else product.apply(v)
+                coeffs = [A[start:start + count].inner(wv)[:, 0] for start, count in runs]
                 for (start, count), r in zip(runs, coeffs):
                     if np.iscomplexobj(r) and not np.iscomplexobj(R):
                         R = R.astype(np.complex128)
