@@ -70,8 +70,14 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
     the QR factorisation it converges to is the same (it is unique), the HBM traffic per pass is the same as
     MGS's (Q is read twice), but a pass costs two host synchronisations instead of one per previous vector,
     which is what makes the orthonormalisation scale over row-sharded GPUs.  Uses only the VectorArray
-    interface (``inner``, ``lincomb``, ``axpy``), so it also runs on pyMOR's own array classes."""
-    assert variant in ('mgs', 'cgs2')
+    interface (``inner``, ``lincomb``, ``axpy``), so it also runs on pyMOR's own array classes.
+    ``'bcgs2'``: :func:`block_gram_schmidt` (panels of vectors against all previous ones through the tensor-core
+    Gramian / lincomb kernels)."""
+    assert variant in ('mgs', 'cgs2', 'bcgs2')
+    if variant == 'bcgs2':
+        return block_gram_schmidt(A, product=product, return_R=return_R, atol=atol, rtol=rtol, offset=offset,
+                                  reiteration_threshold=reiteration_threshold, check=check, check_tol=check_tol,
+                                  copy=copy)
     if copy:
         A = A.copy()
     k = len(A)
@@ -165,6 +171,140 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
             R[i, i] = cur
             weigh(i, 1)
             break
+    if dropped:
+        del A[dropped]
+        R = np.delete(R, dropped, axis=0)
+    if check:
+        m = len(A) - offset
+        err = A[offset:len(A)].inner(A, product)
+        err[:m, offset:len(A)] -= np.eye(m)
+        if err.size > 0:
+            worst = np.max(np.abs(err))
+            if worst >= check_tol:
+                raise AccuracyError(f'result not orthogonal (max err={worst})')
+    return (A, R) if return_R else A
+
+
+def _column_runs(cols):
+    """Maximal runs of consecutive integers in the sorted list ``cols`` as ``(start, count)``: each run is a
+    zero-copy slice view of the array."""
+    runs = []
+    for c in cols:
+        if runs and runs[-1][0] + runs[-1][1] == c:
+            runs[-1][1] += 1
+        else:
+            runs.append([c, 1])
+    return runs
+
+
+def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset=0, panel=32,
+                       reiteration_threshold=9e-1, check=True, check_tol=1e-3, copy=True):
+    """Block classical Gram-Schmidt with re-orthogonalisation (BCGS2) -- the Gram-Schmidt a tensor-core machine
+    wants (not in the reference; same contract as :func:`gram_schmidt`: orthonormal ``Q`` spanning the same
+    nested spaces, upper-triangular ``R`` with ``A = Q R``, vectors of norm <= ``atol`` or numerically dependent
+    on their predecessors removed together with their rows of ``R``).
+
+    The vectors are taken in panels of ``panel`` columns.  A panel ``X`` is projected against all previous
+    vectors ``Q`` at once, ``S = Q^T W X`` (tall-skinny GEMM on the FP64 tensor pipe, ONE host sync, one k x b
+    all-reduce on row-sharded arrays) and ``X -= Q S`` (block lincomb), orthonormalised in itself (classical
+    Gram-Schmidt with re-iteration on the few panel columns: streaming kernels), and the two steps are repeated
+    once ("twice is enough", Barlow & Smoktunowicz 2013: orthogonality O(eps) as long as the input is
+    numerically full rank).  With ``A_P = Q (S1 + S2 R1) + Q_P (R2 R1)`` the factor ``R`` is accumulated on the
+    host.  Work: ~4 n k^2 flop on the tensor cores + O(n k b) streamed bytes, O(k / b) + O(k) host syncs instead
+    of O(k^2) -- the QR factorisation is unique, so ``Q`` and ``R`` agree with modified Gram-Schmidt to rounding
+    x conditioning.  A vector counts as dependent when its norm after the projections is <= ``rtol`` times its
+    norm when it entered the step (the reference compares with the norm of the input vector)."""
+    assert 0 <= offset <= len(A) and panel >= 1
+    if copy:
+        A = A.copy()
+    k = len(A)
+    R = np.eye(k)
+    dropped = []
+    kept = list(range(offset))                         # final, orthonormal columns so far
+
+    def weigh(V):
+        return V if product is None else product.apply(V)
+
+    def project(cols, against):
+        """cols -= Q (Q^T W cols) for Q = A[against]; returns the coefficients (len(against), len(cols))."""
+        X = A[cols[0]:cols[-1] + 1] if cols == list(range(cols[0], cols[-1] + 1)) else A[cols]
+        WX = weigh(X)
+        S = np.zeros((len(against), len(cols)))
+        row = 0
+        for start, count in _column_runs(against):
+            Q = A[start:start + count]
+            C = Q.inner(WX)
+            X.axpy(-1., Q.lincomb(C))
+            S[row:row + count] = C
+            row += count
+        return S
+
+    def orthonormalize_panel(cols):
+        """Classical Gram-Schmidt with re-iteration among the columns ``cols`` themselves (in place).  Returns the
+        kept columns and the (len(kept), len(cols)) triangular factor."""
+        ok, F = [], np.zeros((len(cols), len(cols)))
+        for a, c in enumerate(cols):
+            v = A[c]
+            norm0 = cur = v.norm(product)[0]
+            if norm0 <= atol:
+                dropped.append(c)
+                continue
+            while True:
+                if ok:
+                    wv = weigh(v)
+                    pos = {cc: i for i, cc in enumerate(cols)}
+                    for start, count in _column_runs(ok):
+                        Q = A[start:start + count]
+                        r = Q.inner(wv)[:, 0]
+                        v.axpy(-1., Q.lincomb(r))
+                        F[[pos[cc] for cc in range(start, start + count)], a] += r
+                prev, cur = cur, v.norm(product)[0]
+                if cur <= rtol * norm0:
+                    logger.info('Removing linearly dependent vector %d', c)
+                    dropped.append(c)
+                    break
+                if ok and cur < reiteration_threshold * prev:
+                    continue
+                v.scal(1 / cur)
+                F[a, a] = cur
+                ok.append(c)
+                break
+        rows = [i for i, c in enumerate(cols) if c in ok]
+        return ok, F[rows]
+
+    for p0 in range(offset, k, panel):
+        cols = list(range(p0, min(p0 + panel, k)))
+        norms0 = A[cols[0]:cols[-1] + 1].norm(product)
+        zero = [c for c, nv in zip(cols, norms0) if nv <= atol]
+        dropped.extend(zero)
+        cols = [c for c in cols if c not in zero]
+        if not cols:
+            continue
+        prev_rows = list(kept)
+        if prev_rows:
+            S1 = project(cols, prev_rows)
+            R[np.ix_(prev_rows, cols)] += S1
+            after = A[cols].norm(product) if len(cols) != cols[-1] - cols[0] + 1 else A[cols[0]:cols[-1] + 1].norm(product)
+            gone = [c for c, nv, n0 in zip(cols, after, [norms0[c - p0] for c in cols]) if nv <= rtol * n0]
+            for c in gone:
+                logger.info('Removing linearly dependent vector %d', c)
+            dropped.extend(gone)
+            cols = [c for c in cols if c not in gone]
+            if not cols:
+                continue
+        ok1, R1 = orthonormalize_panel(cols)                     # X = Q1 R1
+        if not ok1:
+            continue
+        if prev_rows:
+            S2 = project(ok1, prev_rows)                         # Q1 = Q S2 + Z
+            ok2, R2 = orthonormalize_panel(ok1)                  # Z = Q2 R2
+            R[np.ix_(prev_rows, cols)] += S2 @ R1
+            R[np.ix_(ok2, cols)] = R2 @ R1
+        else:
+            ok2 = ok1
+            R[np.ix_(ok2, cols)] = R1
+        kept.extend(ok2)
+    dropped = sorted(set(dropped))
     if dropped:
         del A[dropped]
         R = np.delete(R, dropped, axis=0)

@@ -341,6 +341,8 @@ def test_block_gram_schmidt_variant_vs_pymor_mgs(kind):
     Qn, Rn = gram_schmidt(nsp.from_numpy(A.copy()), product=nprod, return_R=True)
     Q1, R1 = alg.gram_schmidt(nsp.from_numpy(A.copy()), product=nprod, return_R=True, variant='cgs2')
     Q2, R2 = alg.gram_schmidt(csp.from_numpy(A), product=cprod, return_R=True, variant='cgs2')
-    for Q, R in ((Q1, R1), (Q2, R2)):
+    Q3, R3 = alg.block_gram_schmidt(nsp.from_numpy(A.copy()), product=nprod, return_R=True, panel=5)
+    Q4, R4 = alg.block_gram_schmidt(csp.from_numpy(A), product=cprod, return_R=True, panel=5)
+    for Q, R in ((Q1, R1), (Q2, R2), (Q3, R3), (Q4, R4)):
         np.testing.assert_allclose(Q.to_numpy(), Qn.to_numpy(), rtol=0, atol=1e-11)
         np.testing.assert_allclose(R, Rn, rtol=0, atol=1e-11)

@@ -108,6 +108,9 @@ def main():
                 Qc, Rc = alg.gram_schmidt(VA, product=prod, return_R=True, variant='cgs2')    # two syncs per pass
                 np.testing.assert_allclose(Rc, Ro, atol=1e-10)
                 np.testing.assert_allclose(Qc.to_numpy(), Qo, atol=1e-10)
+                Qb, Rb = alg.block_gram_schmidt(VA, product=prod, return_R=True, panel=4)     # GEMM-bound panels
+                np.testing.assert_allclose(Rb, Ro, atol=1e-10)
+                np.testing.assert_allclose(Qb.to_numpy(), Qo, atol=1e-10)
             U, s = alg.pod(VA, product=prod, method='method_of_snapshots')
             Uo, so = O.pod(A, w)
             np.testing.assert_allclose(s, so, rtol=1e-10)

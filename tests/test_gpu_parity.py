@@ -636,7 +636,15 @@ def test_mgs_sweep_parity(loaded_lib, rng):
     D = Qc.copy()
     D.axpy(-1.0, Qp)
     assert np.max(D.norm(prod)) < 1e-11
+    Qb, Rb = alg.block_gram_schmidt(A, product=prod, return_R=True, panel=8)      # BCGS2: DMMA Gramian / lincomb panels
+    np.testing.assert_allclose(Rb, Rp, rtol=0, atol=1e-11)
+    assert np.max(np.abs(Qb.gramian(prod) - np.eye(k))) < 1e-13
+    D = Qb.copy()
+    D.axpy(-1.0, Qp)
+    assert np.max(D.norm(prod)) < 1e-11
     for name, gprod in (('euclid', None), ('diag', CudaDiagonalOperator(g['w'], space_of(g['A'].shape[0])))):
         sp_g = space_of(g['A'].shape[0]) if gprod is None else gprod.source
         Q, R = alg.gram_schmidt(sp_g.from_numpy(g['A']), product=gprod, return_R=True, variant='cgs2')
+        assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, None if gprod is None else g['w'], tight=1e-11)
+        Q, R = alg.block_gram_schmidt(sp_g.from_numpy(g['A']), product=gprod, return_R=True, panel=4)
         assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, None if gprod is None else g['w'], tight=1e-11)

@@ -659,3 +659,51 @@ def test_standalone_gram_schmidt_cgs2(emu, rng, name):
         np.testing.assert_allclose(Q1.to_numpy() @ R1, A, atol=1e-11)
         if len(Q1):
             assert np.abs(Q1.gramian(p2) - np.eye(len(Q1))).max() < 1e-13
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
+def test_standalone_block_gram_schmidt(emu, rng, name):
+    """BCGS2: panels against all previous vectors through the Gramian / lincomb entry points, twice; same
+    (unique) QR factorisation, same removed vectors, a handful of launches per panel instead of two per pair."""
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    g = load_golden('gram_schmidt')
+    sp = space_of(g['A'].shape[0])
+    prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp),
+            'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
+    W = {'euclid': None, 'diag': g['w'], 'csr': csr_from(g, 'M')}[name]
+    for panel in (1, 4, 5, 32):
+        VA = sp.from_numpy(g['A'])
+        Q, R = alg.gram_schmidt(VA, product=prod, return_R=True, variant='bcgs2') if panel == 32 else \
+            alg.block_gram_schmidt(VA, product=prod, return_R=True, panel=panel)
+        np.testing.assert_array_equal(VA.to_numpy(), g['A'])
+        assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, W, tight=1e-11)
+        assert np.allclose(np.tril(R[:, :R.shape[0]], -1)[:4, :4], 0)
+    if name == 'euclid':
+        Q0 = alg.gram_schmidt(sp.from_numpy(g['A'][:, :4]), variant='bcgs2')
+        Q0.append(sp.from_numpy(g['A'][:, 10:]))
+        Q1 = alg.block_gram_schmidt(Q0, offset=4, copy=False, panel=3)
+        assert Q1 is Q0
+        np.testing.assert_allclose(Q1.to_numpy(), g['Q_offset'], atol=1e-11)
+    for _ in range(80):
+        dim = int(rng.integers(1, 60))
+        kk = int(rng.integers(1, min(dim, 20) + 1))
+        A = rng.standard_normal((dim, kk))
+        for _ in range(int(rng.integers(0, 3))):
+            j, kind = int(rng.integers(0, kk)), int(rng.integers(0, 3))
+            if kind == 0:
+                A[:, j] = 0
+            elif kind == 1 and j > 0:
+                A[:, j] = A[:, :j] @ rng.standard_normal(j)
+            else:
+                A[:, j] += 5 * A[:, 0]
+        sp2 = space_of(dim)
+        w2 = rng.uniform(0.5, 1.5, dim)
+        p2 = None if name == 'euclid' else CudaDiagonalOperator(w2, sp2)
+        Q0, R0 = alg.gram_schmidt(sp2.from_numpy(A), product=p2, return_R=True)
+        Q1, R1 = alg.block_gram_schmidt(sp2.from_numpy(A), product=p2, return_R=True, panel=int(rng.integers(1, 9)))
+        assert len(Q0) == len(Q1) and R1.shape == R0.shape
+        np.testing.assert_allclose(Q1.to_numpy() @ R1, A, atol=1e-10)
+        if len(Q1):
+            assert np.abs(Q1.gramian(p2) - np.eye(len(Q1))).max() < 1e-12
+            overlap = np.sum(Q1.to_numpy() * ((w2[:, None] if p2 is not None else 1.0) * Q0.to_numpy()), axis=0)
+            np.testing.assert_allclose(overlap, 1.0, atol=1e-6)            # same vectors, same signs

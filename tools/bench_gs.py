@@ -27,8 +27,10 @@ def main():
     ap.add_argument('--dofs', dest='n', type=int, default=10_000_000)
     ap.add_argument('--k', type=int, default=256)
     ap.add_argument('--cpu-n', type=int, default=0, help='also time the oracle on this many rows')
-    ap.add_argument('--variant', default='mgs', choices=['mgs', 'cgs2'],
-                    help="cgs2: block projection per pass (streaming inner + block lincomb), two host syncs per pass")
+    ap.add_argument('--variant', default='mgs', choices=['mgs', 'cgs2', 'bcgs2'],
+                    help="cgs2: block projection per pass (streaming inner + block lincomb), two host syncs per pass; "
+                         "bcgs2: panels of --panel vectors against all previous ones on the tensor cores, twice")
+    ap.add_argument('--panel', type=int, default=32)
     ap.add_argument('--sweep', action='store_true',
                     help='one fused device sweep per pass (pmc_mgs_sweep, in-kernel sums over the GPUs) instead of one '
                          'launch + host sync per pair')
@@ -73,7 +75,12 @@ def main():
         setattr(CudaVectorArrayImpl, name, wrapped)
 
     # warm up the kernels on a small slice
-    alg.gram_schmidt(A[:8].copy(), product=prod, copy=False, sweep=args.sweep, variant=args.variant)
+    def run(arr, **kw):
+        if args.variant == 'bcgs2':
+            return alg.block_gram_schmidt(arr, product=prod, panel=args.panel, copy=False, **kw)
+        return alg.gram_schmidt(arr, product=prod, copy=False, sweep=args.sweep, variant=args.variant, **kw)
+
+    run(A[:8].copy())
     for c in counts:
         counts[c] = 0
     sweep_pairs[0] = 0
@@ -81,12 +88,14 @@ def main():
     torch.cuda.synchronize()
     l0 = space.ctx.launch_count
     t0 = time.perf_counter()
-    Q, R = alg.gram_schmidt(A, product=prod, return_R=True, copy=False, check=False, sweep=args.sweep,
-                            variant=args.variant)
+    Q, R = run(A, return_R=True, check=False)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     launches = space.ctx.launch_count - l0
-    if args.variant == 'cgs2':   # same byte model: projecting onto c columns = c weighted dots + c axpys' worth of traffic
+    if args.variant == 'bcgs2':  # tensor-bound: report seconds; the MGS byte model does not apply
+        pair_steps = k * (k - 1)
+        norms = counts['pairwise_inner']
+    elif args.variant == 'cgs2': # same byte model: projecting onto c columns = c weighted dots + c axpys' worth of traffic
         pair_steps = cgs_cols[0]
         norms = counts['pairwise_inner']
     elif args.sweep:         # same byte model: every swept pair is a weighted dot + an axpy, every sweep ends in a norm
@@ -99,7 +108,7 @@ def main():
     err = float(np.max(np.abs(Q.gramian(prod) - np.eye(len(Q)))))
     peaks = ROOT / 'MEASURED_PEAKS.json'
     hbm = json.loads(peaks.read_text())['hbm_gbs'] if peaks.exists() else 6650.0
-    out = {'workload': f'gram_schmidt {n} x {k}, diag-W, re-iterated', 'fused_sweep': bool(args.sweep), 'variant': args.variant, 'n_gpus': world, 'seconds': dt, 'pair_steps': pair_steps,
+    out = {'workload': f'gram_schmidt {n} x {k}, diag-W, re-iterated', 'fused_sweep': bool(args.sweep), 'variant': args.variant, 'panel': args.panel if args.variant == 'bcgs2' else None, 'n_gpus': world, 'seconds': dt, 'pair_steps': pair_steps,
            'weighted_norms': norms, 'scals': counts['scal'], 'algorithmic_bytes': nbytes,
            'achieved_gbs': nbytes / dt * 1e-9, 'hbm_peak_gbs': hbm,
            'peak_source': 'MEASURED_PEAKS.json' if peaks.exists() else 'fallback 6650 GB/s',
