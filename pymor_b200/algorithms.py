@@ -17,6 +17,10 @@ touch raw data, like their reference counterparts):
 * :func:`inc_vectorarray_hapod`, :func:`dist_vectorarray_hapod` -- src/pymor/algorithms/hapod.py:333, :372
   ("next" row N3)
 * :func:`randomized_range_finder` -- src/pymor/algorithms/rand_la.py:20 ("next" row N2, fixed-size mode)
+* :func:`block_gram_schmidt` (= ``gram_schmidt(variant='bcgs2')``) and ``gram_schmidt(variant='cgs2')`` -- not in
+  the reference: the classical / block-classical Gram-Schmidt variants with re-orthogonalisation that turn the
+  O(k^2) host-synchronised pair-steps of gram_schmidt.py:84-91 into O(k) streaming resp. tensor-core calls; same
+  contract and (the QR factorisation being unique) the same results to rounding x conditioning
 * :func:`ei_greedy`, :func:`deim` -- src/pymor/algorithms/ei.py:30, :182 ("next" row N5: empirical
   interpolation data; the backend sees ``amax`` / ``dofs`` / per-column ``axpy`` / ``norm`` / ``lincomb``)
 """
