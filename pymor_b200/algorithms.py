@@ -210,28 +210,33 @@ def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, 
 
     The vectors are taken in panels of ``panel`` columns.  A panel ``X`` is projected against all previous
     vectors ``Q`` at once, ``S = Q^T W X`` (tall-skinny GEMM on the FP64 tensor pipe, ONE host sync, one k x b
-    all-reduce on row-sharded arrays) and ``X -= Q S`` (block lincomb), orthonormalised in itself (classical
-    Gram-Schmidt with re-iteration on the few panel columns: streaming kernels), and the two steps are repeated
-    once ("twice is enough", Barlow & Smoktunowicz 2013: orthogonality O(eps) as long as the input is
-    numerically full rank).  With ``A_P = Q (S1 + S2 R1) + Q_P (R2 R1)`` the factor ``R`` is accumulated on the
-    host.  Work: ~4 n k^2 flop on the tensor cores + O(n k b) streamed bytes, O(k / b) + O(k) host syncs instead
-    of O(k^2) -- the QR factorisation is unique, so ``Q`` and ``R`` agree with modified Gram-Schmidt to rounding
-    x conditioning.  A vector counts as dependent when its norm after the projections is <= ``rtol`` times its
-    norm when it entered the step (the reference compares with the norm of the input vector)."""
-    assert 0 <= offset <= len(A) and panel >= 1
+    all-reduce on row-sharded arrays) and ``X -= Q S`` (block lincomb), orthonormalised in itself, and the two
+    steps are repeated once ("twice is enough", Barlow & Smoktunowicz 2013: orthogonality O(eps) as long as the
+    input is numerically full rank).  With ``A_P = Q (S1 + S2 R1) + Q_P (R2 R1)`` the factor ``R`` is accumulated
+    on the host.  ``panel`` may be a tuple, e.g. ``(128, 16)``: a panel is then orthonormalised in itself by the
+    same scheme with the next size (128-wide panels keep the 128 x 128 tensor-core tiles full, 16-wide
+    sub-panels keep the innermost work small); the innermost panels use classical Gram-Schmidt with
+    re-iteration, vector by vector, on the streaming kernels.  Work: ~4 n k^2 flop on the tensor cores +
+    O(n k b) streamed bytes, O(k) host syncs instead of O(k^2) -- the QR factorisation is unique, so ``Q`` and
+    ``R`` agree with modified Gram-Schmidt to rounding x conditioning.  A vector counts as dependent when its
+    norm after the projections is <= ``rtol`` times its norm when it entered the step (the reference compares
+    with the norm of the input vector)."""
+    panels = tuple(int(b) for b in (panel if isinstance(panel, (tuple, list)) else (panel,)))
+    assert 0 <= offset <= len(A) and all(b >= 1 for b in panels)
     if copy:
         A = A.copy()
     k = len(A)
-    R = np.eye(k)
     dropped = []
-    kept = list(range(offset))                         # final, orthonormal columns so far
 
     def weigh(V):
         return V if product is None else product.apply(V)
 
+    def view(cols):
+        return A[cols[0]:cols[-1] + 1] if len(cols) == cols[-1] - cols[0] + 1 else A[cols]
+
     def project(cols, against):
         """cols -= Q (Q^T W cols) for Q = A[against]; returns the coefficients (len(against), len(cols))."""
-        X = A[cols[0]:cols[-1] + 1] if cols == list(range(cols[0], cols[-1] + 1)) else A[cols]
+        X = view(cols)
         WX = weigh(X)
         S = np.zeros((len(against), len(cols)))
         row = 0
@@ -243,10 +248,11 @@ def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, 
             row += count
         return S
 
-    def orthonormalize_panel(cols):
+    def vector_loop(cols):
         """Classical Gram-Schmidt with re-iteration among the columns ``cols`` themselves (in place).  Returns the
         kept columns and the (len(kept), len(cols)) triangular factor."""
         ok, F = [], np.zeros((len(cols), len(cols)))
+        pos = {c: i for i, c in enumerate(cols)}
         for a, c in enumerate(cols):
             v = A[c]
             norm0 = cur = v.norm(product)[0]
@@ -256,7 +262,6 @@ def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, 
             while True:
                 if ok:
                     wv = weigh(v)
-                    pos = {cc: i for i, cc in enumerate(cols)}
                     for start, count in _column_runs(ok):
                         Q = A[start:start + count]
                         r = Q.inner(wv)[:, 0]
@@ -273,41 +278,63 @@ def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, 
                 F[a, a] = cur
                 ok.append(c)
                 break
-        rows = [i for i, c in enumerate(cols) if c in ok]
-        return ok, F[rows]
+        return ok, F[[pos[c] for c in ok]]
 
-    for p0 in range(offset, k, panel):
-        cols = list(range(p0, min(p0 + panel, k)))
-        norms0 = A[cols[0]:cols[-1] + 1].norm(product)
-        zero = [c for c, nv in zip(cols, norms0) if nv <= atol]
-        dropped.extend(zero)
-        cols = [c for c in cols if c not in zero]
-        if not cols:
-            continue
-        prev_rows = list(kept)
-        if prev_rows:
-            S1 = project(cols, prev_rows)
-            R[np.ix_(prev_rows, cols)] += S1
-            after = A[cols].norm(product) if len(cols) != cols[-1] - cols[0] + 1 else A[cols[0]:cols[-1] + 1].norm(product)
-            gone = [c for c, nv, n0 in zip(cols, after, [norms0[c - p0] for c in cols]) if nv <= rtol * n0]
-            for c in gone:
-                logger.info('Removing linearly dependent vector %d', c)
-            dropped.extend(gone)
-            cols = [c for c in cols if c not in gone]
-            if not cols:
+    def orthonormalize(cols, level, before=()):
+        """Orthonormalise the columns ``cols`` (in place) against the final columns ``before`` and among
+        themselves with panels of ``panels[level]`` columns.  Returns the kept columns ``ok`` and the factor ``F`` of
+        shape (len(before) + len(ok), len(cols)): ``A_cols(input) = A[before + ok] F``."""
+        if level >= len(panels) or (not before and len(cols) <= panels[-1] and level > 0):
+            assert not before
+            return vector_loop(cols)
+        b = panels[level]
+        done = list(before)
+        pos = {c: i for i, c in enumerate(cols)}
+        F = np.zeros((len(before) + len(cols), len(cols)))       # rows: `before`, then one per column of `cols`
+        row_of = {c: i for i, c in enumerate(before)}
+        row_of.update({c: len(before) + i for i, c in enumerate(cols)})
+        for p0 in range(0, len(cols), b):
+            P = cols[p0:p0 + b]
+            norms0 = view(P).norm(product)
+            zero = [c for c, nv in zip(P, norms0) if nv <= atol]
+            dropped.extend(zero)
+            n0 = {c: nv for c, nv in zip(P, norms0)}
+            P = [c for c in P if c not in zero]
+            if not P:
                 continue
-        ok1, R1 = orthonormalize_panel(cols)                     # X = Q1 R1
-        if not ok1:
-            continue
-        if prev_rows:
-            S2 = project(ok1, prev_rows)                         # Q1 = Q S2 + Z
-            ok2, R2 = orthonormalize_panel(ok1)                  # Z = Q2 R2
-            R[np.ix_(prev_rows, cols)] += S2 @ R1
-            R[np.ix_(ok2, cols)] = R2 @ R1
-        else:
-            ok2 = ok1
-            R[np.ix_(ok2, cols)] = R1
-        kept.extend(ok2)
+            prev = list(done)
+            if prev:
+                S1 = project(P, prev)
+                F[np.ix_([row_of[c] for c in prev], [pos[c] for c in P])] += S1
+                gone = [c for c, nv in zip(P, view(P).norm(product)) if nv <= rtol * n0[c]]
+                for c in gone:
+                    logger.info('Removing linearly dependent vector %d', c)
+                dropped.extend(gone)
+                P = [c for c in P if c not in gone]
+                if not P:
+                    continue
+            ok1, R1 = orthonormalize(P, level + 1)                       # X = Q1 R1
+            if not ok1:
+                continue
+            if prev:
+                S2 = project(ok1, prev)                                   # Q1 = Q S2 + Z
+                ok2, R2 = orthonormalize(ok1, level + 1)                 # Z = Q2 R2
+                F[np.ix_([row_of[c] for c in prev], [pos[c] for c in P])] += S2 @ R1
+                F[np.ix_([row_of[c] for c in ok2], [pos[c] for c in P])] = R2 @ R1
+            else:
+                ok2 = ok1
+                F[np.ix_([row_of[c] for c in ok2], [pos[c] for c in P])] = R1
+            done.extend(ok2)
+        ok = done[len(before):]
+        return ok, F[[row_of[c] for c in list(before) + ok]]
+
+    cols = list(range(offset, k))
+    R = np.eye(k)
+    if cols:
+        before = list(range(offset))
+        ok, F = orthonormalize(cols, 0, before)
+        R[:, offset:] = 0.
+        R[np.ix_(before + ok, cols)] = F
     dropped = sorted(set(dropped))
     if dropped:
         del A[dropped]

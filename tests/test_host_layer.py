@@ -671,7 +671,7 @@ def test_standalone_block_gram_schmidt(emu, rng, name):
     prod = {'euclid': None, 'diag': CudaDiagonalOperator(g['w'], sp),
             'csr': CudaCsrOperator(csr_from(g, 'M'), sp)}[name]
     W = {'euclid': None, 'diag': g['w'], 'csr': csr_from(g, 'M')}[name]
-    for panel in (1, 4, 5, 32):
+    for panel in (1, 4, 5, 32, (8, 2), (6, 3, 2)):
         VA = sp.from_numpy(g['A'])
         Q, R = alg.gram_schmidt(VA, product=prod, return_R=True, variant='bcgs2') if panel == 32 else \
             alg.block_gram_schmidt(VA, product=prod, return_R=True, panel=panel)
@@ -700,7 +700,8 @@ def test_standalone_block_gram_schmidt(emu, rng, name):
         w2 = rng.uniform(0.5, 1.5, dim)
         p2 = None if name == 'euclid' else CudaDiagonalOperator(w2, sp2)
         Q0, R0 = alg.gram_schmidt(sp2.from_numpy(A), product=p2, return_R=True)
-        Q1, R1 = alg.block_gram_schmidt(sp2.from_numpy(A), product=p2, return_R=True, panel=int(rng.integers(1, 9)))
+        panel = [int(rng.integers(1, 9)), (8, 3), (16, 4, 2), (5, 5)][int(rng.integers(0, 4))]
+        Q1, R1 = alg.block_gram_schmidt(sp2.from_numpy(A), product=p2, return_R=True, panel=panel)
         assert len(Q0) == len(Q1) and R1.shape == R0.shape
         np.testing.assert_allclose(Q1.to_numpy() @ R1, A, atol=1e-10)
         if len(Q1):

@@ -30,7 +30,7 @@ def main():
     ap.add_argument('--variant', default='mgs', choices=['mgs', 'cgs2', 'bcgs2'],
                     help="cgs2: block projection per pass (streaming inner + block lincomb), two host syncs per pass; "
                          "bcgs2: panels of --panel vectors against all previous ones on the tensor cores, twice")
-    ap.add_argument('--panel', type=int, default=32)
+    ap.add_argument('--panel', default='32', help='panel width(s) of bcgs2, outermost first, e.g. 128,16')
     ap.add_argument('--sweep', action='store_true',
                     help='one fused device sweep per pass (pmc_mgs_sweep, in-kernel sums over the GPUs) instead of one '
                          'launch + host sync per pair')
@@ -77,7 +77,8 @@ def main():
     # warm up the kernels on a small slice
     def run(arr, **kw):
         if args.variant == 'bcgs2':
-            return alg.block_gram_schmidt(arr, product=prod, panel=args.panel, copy=False, **kw)
+            return alg.block_gram_schmidt(arr, product=prod, panel=tuple(int(b) for b in args.panel.split(',')),
+                                          copy=False, **kw)
         return alg.gram_schmidt(arr, product=prod, copy=False, sweep=args.sweep, variant=args.variant, **kw)
 
     run(A[:8].copy())
