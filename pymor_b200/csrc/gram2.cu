@@ -12,6 +12,10 @@
 //  * partially filled blocks (k not a multiple of 32) run only their 8-row / 8-column sub-blocks that
 //    hold data, through compile-time specialisations of the stage loop (no predicated DMMA), and are
 //    spread over the four SMSPs;
+//  * tiles with fewer than 16 blocks of data -- narrow operands such as a panel of block Gram-Schmidt or a
+//    few right-hand sides, and the last tile row of a ragged k -- split the K range of every block 4 or 2
+//    ways over the otherwise idle warps (each part writes its own slot of the partial tile, the reduction
+//    adds them): a 128 x 32 tile keeps all 16 warps and all four tensor pipes busy instead of 4;
 //  * the diagonal weight is applied ONCE per stage in shared memory (each warp scales 1/16 of the B tile
 //    three stages ahead: 4 DMUL per warp and stage) instead of on every warp's fragments (16 DMUL per
 //    warp and stage).  For diagonal tiles the scaled copy goes to the B slot the tile does not load.
@@ -53,8 +57,9 @@ __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *
     }
 }
 
-// shape codes of the warp-uniform dispatch in the stage loop
-constexpr int SHAPE_IDLE = -1, SHAPE_TRI = 32, SHAPE_HALF = 64;   // rectangular: (nm-1)*4 + (nn-1)
+// shape codes of the warp-uniform dispatch in the stage loop: rectangular blocks (nm-1)*4 + (nn-1), + 16 when the
+// warp contracts half of the stage (2 quarter-steps), + 32 for a quarter; triangular (diagonal) blocks 48 + nm-1
+constexpr int SHAPE_IDLE = -1, SHAPE_TRI = 48;
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -85,8 +90,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const G2Plan plan = g2_plan(warp, diag, vm, vn, p.opts);
     const int shape = !plan.active ? SHAPE_IDLE
                       : plan.tri   ? SHAPE_TRI + plan.nm - 1
-                      : plan.nks == 2 ? SHAPE_HALF
-                                      : (plan.nm - 1) * 4 + (plan.nn - 1);
+                                   : (plan.nm - 1) * 4 + (plan.nn - 1) + (plan.nks == 4 ? 0 : plan.nks == 2 ? 16 : 32);
 
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
@@ -171,8 +175,10 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const double *a_s = sA + s * TILE_ELEMS + rowA;
         const double *b_s = b_base + s * TILE_ELEMS + rowB;
         switch (shape) {
-#define G2_RECT(NM, NN) \
-    case (NM - 1) * 4 + (NN - 1): stage_mma<NM, NN, false, 4>(acc, a_s, b_s, fo); break;
+#define G2_RECT(NM, NN)                                                                                   \
+    case (NM - 1) * 4 + (NN - 1): stage_mma<NM, NN, false, 4>(acc, a_s, b_s, fo); break;                  \
+    case (NM - 1) * 4 + (NN - 1) + 16: stage_mma<NM, NN, false, 2>(acc, a_s, b_s, fo); break;             \
+    case (NM - 1) * 4 + (NN - 1) + 32: stage_mma<NM, NN, false, 1>(acc, a_s, b_s, fo); break;
             G2_RECT(4, 4) G2_RECT(4, 3) G2_RECT(4, 2) G2_RECT(4, 1)
             G2_RECT(3, 4) G2_RECT(3, 3) G2_RECT(3, 2) G2_RECT(3, 1)
             G2_RECT(2, 4) G2_RECT(2, 3) G2_RECT(2, 2) G2_RECT(2, 1)
@@ -182,7 +188,6 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             case SHAPE_TRI + 2: stage_mma<3, 3, true, 4>(acc, a_s, b_s, fo); break;
             case SHAPE_TRI + 1: stage_mma<2, 2, true, 4>(acc, a_s, b_s, fo); break;
             case SHAPE_TRI + 0: stage_mma<1, 1, true, 4>(acc, a_s, b_s, fo); break;
-            case SHAPE_HALF: stage_mma<4, 4, false, 2>(acc, a_s, b_s, fo); break;
             default: break;
         }
         if (WEIGHTED && kt + LOOKAHEAD < nk) scale_stage(kt + LOOKAHEAD);
@@ -204,8 +209,8 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-// stage 2: out[i + j*ldo] = sum_split partial[split][tile][j][i]  (+ the mirrored K-half of split blocks,
-// + mirror for SYRK).  Fixed order => bitwise reproducible.
+// stage 2: out[i + j*ldo] = sum over the splits of (sum over the K parts of the entry's block), mirrored for SYRK.
+// Fixed order => bitwise reproducible.
 __global__ void gram2_reduce_kernel(const double *__restrict__ partials, int nsplit, GramParams p,
                                     double *__restrict__ out, int64_t ldo, int accumulate) {
     const int tile = blockIdx.y;
@@ -221,13 +226,29 @@ __global__ void gram2_reduce_kernel(const double *__restrict__ partials, int nsp
     const size_t tile_elems = (size_t)BM * BN;
     const double *src = partials + (size_t)tile * tile_elems;
     const size_t step = (size_t)p.ntiles * tile_elems;
-    const int vm = min(BM, p.kA - ti * BM);
-    const bool two = diag && g2_is_split_block(il >> 5, jl >> 5, vm, p.opts);
-    const int e2 = two ? g2_mirror_index(il, jl) : e;
+    const int vm = min(BM, p.kA - ti * BM), vn = min(BN, p.kB - tj * BN);
+    // Where the entry's K parts were stored (up to 4 partial-tile entries): diagonal tiles keep a block in place
+    // (+ the transposed slot for the second half of a split block); other tiles number their (block, K part)
+    // units and store unit u in slot u.
+    int src_idx[4], parts = 1;
+    src_idx[0] = e;
+    if (diag) {
+        if (g2_is_split_block(il >> 5, jl >> 5, vm, p.opts)) {
+            parts = 2;
+            src_idx[1] = g2_mirror_index(il, jl);
+        }
+    } else {
+        int first;
+        g2_general_sources(il, jl, vm, vn, p.opts, first, parts);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) src_idx[q] = g2_slot_index(first + (q < parts ? q : 0), il, jl);
+    }
     double s = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) {
-        double v = src[(size_t)sp * step + e];
-        if (two) v += src[(size_t)sp * step + e2];
+        const double *t = src + (size_t)sp * step;
+        double v = t[src_idx[0]];
+        if (parts > 1) v += t[src_idx[1]];
+        if (parts > 2) v = (v + t[src_idx[2]]) + t[src_idx[3]];
         s += v;
     }
     if (accumulate) s += out[gi + (int64_t)gj * ldo];

@@ -27,10 +27,12 @@ constexpr int G2_OPT_NO_RAGGED = 128;  // partially filled blocks run in full
 //   nm, nn    8-row / 8-column sub-blocks of it that hold data (1..4)
 //   ks0, nks  quarter-steps (4 rows of the 16-row stage each) this warp contracts: [ks0, ks0+nks)
 //   tri       diagonal block of a diagonal SYRK tile: only sub-blocks (mi, ni) with ni <= mi
-//   mirror    second K-half of a split block: the accumulators go to the transposed block slot
-//             (wn, wm) of the partial tile, which a diagonal tile does not use otherwise
+//   sm, sn    32x32 slot of the partial tile that receives the accumulators.  A block whose K range is
+//             split over several warps occupies several slots (the reduction adds them): slots of blocks
+//             the tile does not have -- the upper triangle of a diagonal tile, the empty block rows /
+//             columns of a narrow tile.
 struct G2Plan {
-    int wm, wn, nm, nn, ks0, nks, tri, mirror, active;
+    int wm, wn, nm, nn, ks0, nks, tri, sm, sn, active;
 };
 
 G2_HD int g2_min(int a, int b) { return a < b ? a : b; }
@@ -56,16 +58,34 @@ G2_HD bool g2_is_split_block(int wm, int wn, int vm, int opts) {
     return g2_sub_blocks(vm, wm, opts) == 4 && g2_sub_blocks(vm, wn, opts) == 4;
 }
 
+// Off-diagonal / general tiles: bm x bn blocks hold data (narrow operands -- a panel of a block
+// Gram-Schmidt, a few right-hand sides, the last tile row of a ragged k -- have fewer than 16).  Then the K
+// range of every block is split f = 4 or 2 ways so that (almost) all 16 warps and all four FP64 tensor
+// pipes work: unit u = block * f + part runs on warp u and writes slot u of the partial tile.
+// Blocks are numbered so that the blocks of a SHORT block row (ragged M) sit on four different SMSPs (n_fast: the
+// block column runs fastest); a short block column (ragged N) is spread by the default numbering.
+G2_HD void g2_tile_shape(int vm, int vn, int opts, int &bm, int &bn, int &f, int &n_fast) {
+    bm = g2_min(4, (vm + 31) >> 5);
+    bn = g2_min(4, (vn + 31) >> 5);
+    f = 1;
+    if (!(opts & G2_OPT_NO_KSPLIT)) {
+        if (bm * bn * 4 <= G2_WARPS) f = 4;
+        else if (bm * bn * 2 <= G2_WARPS) f = 2;
+    }
+    n_fast = (vm & 31) != 0 ? 1 : 0;
+}
+G2_HD int g2_block_number(int wm, int wn, int bm, int bn, int n_fast) { return n_fast ? wn + bn * wm : wm + bm * wn; }
+
 // Diagonal SYRK tiles need the 10 blocks on/below the diagonal.  Each SMSP (warp % 4) has its own
 // FP64 tensor pipe, so the work is dealt out per SMSP: one diagonal block (10 of 16 sub-blocks),
 // one full off-diagonal block and one K-half of a split off-diagonal block -- 2.125 block units
-// per SMSP instead of 4 for a full tile.  Other tiles: 4x4 blocks, one per warp; when the tile is
-// short in M the warps of one block row sit on four different SMSPs (transposed map), so that the
-// cheaper last block row shortens the whole tile.
+// per SMSP instead of 4 for a full tile.  Other tiles: see g2_tile_shape; consecutive units sit on
+// different SMSPs, so short (ragged) blocks and K parts spread evenly.
 G2_HD G2Plan g2_plan(int warp, bool diag, int vm, int vn, int opts) {
     G2Plan p;
-    p.ks0 = 0; p.nks = 4; p.tri = 0; p.mirror = 0; p.active = 1;
+    p.ks0 = 0; p.nks = 4; p.tri = 0; p.active = 1;
     if (diag) {
+        int mirror = 0;
         if (warp < 4) {
             p.wm = p.wn = warp;
             p.tri = (opts & G2_OPT_NO_TRI) ? 0 : 1;
@@ -75,7 +95,7 @@ G2_HD G2Plan g2_plan(int warp, bool diag, int vm, int vn, int opts) {
             g2_lower_block(4 + ((warp - 8) >> 1), p.wm, p.wn);
             const int half = (warp - 8) & 1;
             if (g2_is_split_block(p.wm, p.wn, vm, opts)) {
-                p.ks0 = 2 * half; p.nks = 2; p.mirror = half;
+                p.ks0 = 2 * half; p.nks = 2; mirror = half;
             } else if (half) {
                 p.active = 0;
             }
@@ -83,10 +103,23 @@ G2_HD G2Plan g2_plan(int warp, bool diag, int vm, int vn, int opts) {
             p.wm = p.wn = 0;
             p.active = 0;
         }
+        p.sm = mirror ? p.wn : p.wm;          // second K-half: the transposed slot, unused by a diagonal tile
+        p.sn = mirror ? p.wm : p.wn;
     } else {
-        const bool transposed = (opts & G2_OPT_NO_RAGGED) ? (vm <= G2_BM - 32) : (vm < G2_BM);
-        if (transposed) { p.wm = warp >> 2; p.wn = warp & 3; }
-        else            { p.wm = warp & 3;  p.wn = warp >> 2; }
+        int bm, bn, f, n_fast;
+        g2_tile_shape(vm, vn, opts, bm, bn, f, n_fast);
+        const int block = warp / f, part = warp % f;
+        if (block >= bm * bn) {
+            p.wm = p.wn = 0;
+            p.active = 0;
+        } else {
+            p.wm = n_fast ? block / bn : block % bm;
+            p.wn = n_fast ? block % bn : block / bm;
+            p.nks = 4 / f;
+            p.ks0 = part * p.nks;
+        }
+        p.sm = warp & 3;
+        p.sn = warp >> 2;
     }
     p.nm = g2_sub_blocks(vm, p.wm, opts);
     p.nn = g2_sub_blocks(vn, p.wn, opts);
@@ -112,19 +145,30 @@ G2_HD int g2_frag_offset(int ks, int lane) {
 }
 G2_HD int g2_frag_row(int wblk, int sub, int lane) { return wblk * 32 + sub * 8 + g2_rho(lane >> 2); }
 
-// Accumulator c (0/1) of sub-block (mi, ni) of lane: element (i, j) of the 128x128 partial tile,
-// stored column-major [j][i].
+// Accumulator c (0/1) of sub-block (mi, ni) of lane: element of the 128x128 partial tile, stored
+// column-major [j][i], inside the warp's slot.
 G2_HD int g2_out_index(const G2Plan &p, int mi, int ni, int lane, int c) {
-    const int om = p.mirror ? p.wn : p.wm, on = p.mirror ? p.wm : p.wn;
-    const int i = om * 32 + mi * 8 + g2_rho(lane >> 2);
-    const int j = on * 32 + ni * 8 + g2_rho(2 * (lane & 3) + c);
+    const int i = p.sm * 32 + mi * 8 + g2_rho(lane >> 2);
+    const int j = p.sn * 32 + ni * 8 + g2_rho(2 * (lane & 3) + c);
     return j * G2_BM + i;
 }
 
-// Where the second K-half of element (il, jl) of a diagonal tile was stored (see `mirror`)
+// Where the second K-half of element (il, jl) of a diagonal tile was stored (the transposed slot)
 G2_HD int g2_mirror_index(int il, int jl) {
     const int i2 = (jl >> 5) * 32 + (il & 31), j2 = (il >> 5) * 32 + (jl & 31);
     return j2 * G2_BM + i2;
+}
+
+// Off-diagonal / general tile: element (il, jl) of the tile is the sum of the entries g2_slot_index(slot, il, jl)
+// of the slots first .. first+count-1 (one per K part of its block).
+G2_HD void g2_general_sources(int il, int jl, int vm, int vn, int opts, int &first, int &count) {
+    int bm, bn, f, n_fast;
+    g2_tile_shape(vm, vn, opts, bm, bn, f, n_fast);
+    first = g2_block_number(il >> 5, jl >> 5, bm, bn, n_fast) * f;   // units first .. first+f-1 = slots of the same number
+    count = f;
+}
+G2_HD int g2_slot_index(int slot, int il, int jl) {
+    return ((slot >> 2) * 32 + (jl & 31)) * G2_BM + (slot & 3) * 32 + (il & 31);
 }
 
 // Diagonal weight: warp `warp` scales tile rows 8*warp .. 8*warp+7 of a stage, two 16-byte chunks

@@ -157,19 +157,30 @@ extern "C" int g2_model_gram(const double *A, int64_t csA, int kA, const double 
         int ti, tj;
         decode_tile(p, tile, ti, tj);
         const bool diag = symmetric && ti == tj;
-        const int vm = g2_min(G2_BM, kA - ti * G2_BM);
+        const int vm = g2_min(G2_BM, kA - ti * G2_BM), vn = g2_min(G2_BN, kB - tj * G2_BN);
         for (int e = 0; e < G2_BM * G2_BN; ++e) {
             const int il = e % G2_BM, jl = e / G2_BM;
             const int gi = ti * G2_BM + il, gj = tj * G2_BN + jl;
             if (gi >= kA || gj >= kB) continue;
             if (diag && gi < gj) continue;
-            const bool two = diag && g2_is_split_block(il >> 5, jl >> 5, vm, opts);
-            const int e2 = two ? g2_mirror_index(il, jl) : e;
+            int src_idx[4], parts = 1;
+            src_idx[0] = e;
+            if (diag) {
+                if (g2_is_split_block(il >> 5, jl >> 5, vm, opts)) {
+                    parts = 2;
+                    src_idx[1] = g2_mirror_index(il, jl);
+                }
+            } else {
+                int first;
+                g2_general_sources(il, jl, vm, vn, opts, first, parts);
+                for (int q = 0; q < 4; ++q) src_idx[q] = g2_slot_index(first + (q < parts ? q : 0), il, jl);
+            }
             double s = 0.0;
             for (int64_t sp = 0; sp < nsplit; ++sp) {
                 const double *src = partials.data() + ((size_t)sp * p.ntiles + tile) * tile_elems;
-                double v = src[e];
-                if (two) v += src[e2];
+                double v = src[src_idx[0]];
+                if (parts > 1) v += src[src_idx[1]];
+                if (parts > 2) v = (v + src[src_idx[2]]) + src[src_idx[3]];
                 s += v;
             }
             out[gi + (int64_t)gj * ldo] = s;

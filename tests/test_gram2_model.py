@@ -60,9 +60,10 @@ def test_syrk_model(model, rng, k, weighted, opts):
     np.testing.assert_allclose(G, ref, rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize('opts', [G2_ENABLE, G2_ENABLE | G2_NO_RAGGED])
+@pytest.mark.parametrize('opts', [G2_ENABLE, G2_ENABLE | G2_NO_RAGGED, G2_ENABLE | G2_NO_KSPLIT])
 @pytest.mark.parametrize('weighted', [False, True])
-@pytest.mark.parametrize('ka,kb', [(17, 130), (130, 17), (128, 128), (129, 257), (200, 64), (100, 100), (250, 250)])
+@pytest.mark.parametrize('ka,kb', [(17, 130), (130, 17), (128, 128), (129, 257), (200, 64), (100, 100), (250, 250),
+                                   (224, 32), (32, 224), (128, 8), (300, 20), (40, 40), (64, 128), (16, 16)])
 def test_general_inner_model(model, rng, ka, kb, weighted, opts):
     n = 53
     A, B = rng.standard_normal((n, ka)), rng.standard_normal((n, kb))
@@ -241,3 +242,17 @@ def test_barrier_protocol_simulation(rng, weighted, diag):
     for nk in (1, 2, 3, 4, 6, 7, 13, 40):
         for _ in range(6):
             _simulate_protocol(nk, weighted, diag, rng)
+
+
+def test_narrow_tiles_use_all_warps(model, rng):
+    """A 128 x 32 tile (a panel of block Gram-Schmidt against 128 previous vectors) has 4 blocks of data: their K
+    range is split four ways, so all 16 warps work and every SMSP issues the same 64 DMMA per stage; a 128 x 64
+    tile splits two ways; with the split disabled the same work sits on 4 (8) warps."""
+    n = 40
+    A, B = rng.standard_normal((n, 128)), rng.standard_normal((n, 32))
+    for kb, opts in ((32, G2_ENABLE), (64, G2_ENABLE), (32, G2_ENABLE | G2_NO_KSPLIT)):
+        B = rng.standard_normal((n, kb))
+        counts = np.zeros((1, 4), dtype=np.int64)
+        G = run_model(model, A, B, None, False, opts, 48, counts)
+        np.testing.assert_allclose(G, A.T @ B, rtol=0, atol=1e-12)
+        assert (counts[0] == 16 * kb // 8).all(), counts          # 4 (8) blocks x 64 DMMA over the four SMSPs
