@@ -39,8 +39,10 @@ timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --variant cgs2 > gp
 grep -hE '^\{' gpurun_out/r02_gs_10Mx256_cgs2.log | cut -c1-500
 timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --variant bcgs2 > gpurun_out/r02_gs_10Mx256_bcgs2.log 2>&1
 timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --variant bcgs2 --panel 128,16 > gpurun_out/r02_gs_10Mx256_bcgs2_128_16.log 2>&1
+timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --variant bcgs2 --panel 32,8 > gpurun_out/r02_gs_10Mx256_bcgs2_32_8.log 2>&1
 grep -hE '^\{' gpurun_out/r02_gs_10Mx256_bcgs2.log | cut -c1-500
 grep -hE '^\{' gpurun_out/r02_gs_10Mx256_bcgs2_128_16.log | cut -c1-500
+grep -hE '^\{' gpurun_out/r02_gs_10Mx256_bcgs2_32_8.log | cut -c1-500
 timeout 300 python tools/bench_cholqr.py --dofs 10000000 --k 256 > gpurun_out/r02_cholqr_10Mx256.log 2>&1
 grep -hE '^\{' gpurun_out/r02_cholqr_10Mx256.log | cut -c1-400
 # HBM-bound kernels: 10M-DOF vectors, 12 columns -> a few hundred launches; capture a handful of each kind

@@ -18,8 +18,10 @@ timeout 600 $TR tools/bench_gs.py --dofs 10000000 --k 256 --variant cgs2 > gpuru
 grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_cgs2.log | cut -c1-500
 timeout 600 $TR tools/bench_gs.py --dofs 10000000 --k 256 --variant bcgs2 > gpurun_out/r02_gs_${N}gpu_bcgs2.log 2>&1
 timeout 600 $TR tools/bench_gs.py --dofs 10000000 --k 256 --variant bcgs2 --panel 128,16 > gpurun_out/r02_gs_${N}gpu_bcgs2_128_16.log 2>&1
+timeout 600 $TR tools/bench_gs.py --dofs 10000000 --k 256 --variant bcgs2 --panel 32,8 > gpurun_out/r02_gs_${N}gpu_bcgs2_32_8.log 2>&1
 grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_bcgs2.log | cut -c1-500
 grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_bcgs2_128_16.log | cut -c1-500
+grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_bcgs2_32_8.log | cut -c1-500
 timeout 600 $TR tools/bench_cholqr.py --dofs 10000000 --k 256 > gpurun_out/r02_cholqr_${N}gpu.log 2>&1
 grep -hE '^\{' gpurun_out/r02_cholqr_${N}gpu.log | cut -c1-400
 timeout 1200 $TR bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r02_bench_${N}gpu.log 2>&1
