@@ -380,11 +380,16 @@ def method_of_snapshots(A, product=None, modes=None, rtol=1e-7, atol=0., l2_err=
     return A.lincomb(V / s), s, V.conj().T
 
 
-def qr_svd(A, product=None, modes=None, rtol=4e-8, atol=0., l2_err=0.):
-    """SVD of ``A`` through Gram-Schmidt QR and the SVD of the small ``R`` factor."""
+def qr_svd(A, product=None, modes=None, rtol=4e-8, atol=0., l2_err=0., gs_variant='mgs'):
+    """SVD of ``A`` through Gram-Schmidt QR and the SVD of the small ``R`` factor.
+
+    ``gs_variant`` (not in the reference): the Gram-Schmidt variant of :func:`gram_schmidt` used for the QR step.
+    ``'bcgs2'`` runs it on the tensor cores (~4 n k^2 flop, O(k) host syncs) instead of k(k-1) host-synchronised
+    pair-steps -- the POD that does NOT square the condition number then costs about as much as the method of
+    snapshots."""
     if A.dim == 0 or len(A) == 0:
         return A.space.empty(), np.array([]), np.zeros((0, len(A)))
-    Q, R = gram_schmidt(A, product=product, return_R=True, check=False)
+    Q, R = gram_schmidt(A, product=product, return_R=True, check=False, variant=gs_variant)
     U2, s, Vh = spla.svd(R, lapack_driver='gesvd')
     m = _select_modes(s, modes, rtol, atol, l2_err)
     return Q.lincomb(U2[:, :m]), s[:m], Vh[:m]
@@ -394,12 +399,13 @@ SVD_VA_METHODS = {'method_of_snapshots': method_of_snapshots, 'qr_svd': qr_svd}
 
 
 def pod(A, product=None, modes=None, rtol=1e-7, atol=0., l2_err=0., method='qr_svd', orth_tol=1e-10,
-        return_reduced_coefficients=False):
+        return_reduced_coefficients=False, **method_options):
     """Proper orthogonal decomposition of ``A``; re-orthonormalises the modes with
-    :func:`gram_schmidt` when their orthogonality error is not below ``orth_tol``."""
+    :func:`gram_schmidt` when their orthogonality error is not below ``orth_tol``.  ``method_options`` (not in
+    the reference) are handed to the SVD method, e.g. ``method='qr_svd', gs_variant='bcgs2'``."""
     assert method in SVD_VA_METHODS
     modes_va, svals, coeffs = SVD_VA_METHODS[method](A, product=product, modes=modes, rtol=rtol, atol=atol,
-                                                     l2_err=l2_err)
+                                                     l2_err=l2_err, **method_options)
     if modes_va.dim > 0 and len(modes_va) > 0 and np.isfinite(orth_tol):
         err = np.max(np.abs(modes_va.inner(modes_va, product) - np.eye(len(modes_va))))
         if err >= orth_tol:

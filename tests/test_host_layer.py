@@ -708,3 +708,22 @@ def test_standalone_block_gram_schmidt(emu, rng, name):
             assert np.abs(Q1.gramian(p2) - np.eye(len(Q1))).max() < 1e-12
             overlap = np.sum(Q1.to_numpy() * ((w2[:, None] if p2 is not None else 1.0) * Q0.to_numpy()), axis=0)
             np.testing.assert_allclose(overlap, 1.0, atol=1e-6)            # same vectors, same signs
+
+
+@pytest.mark.parametrize('name', ['euclid', 'diag'])
+def test_pod_qr_svd_with_block_gram_schmidt(emu, name):
+    """pod(method='qr_svd', gs_variant='bcgs2'): the reference's default POD method with the QR step on the
+    tensor-core kernels -- same singular values and subspace as the reference's result."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    g = load_golden('pod')
+    A = g['A']
+    sp = space_of(A.shape[0])
+    W = None if name == 'euclid' else g['w']
+    prod = None if name == 'euclid' else CudaDiagonalOperator(g['w'], sp)
+    U_ref, s_ref = O.pod(A, W, method='qr_svd')
+    for variant in ('mgs', 'cgs2', 'bcgs2'):
+        U, s = alg.pod(sp.from_numpy(A), product=prod, method='qr_svd', gs_variant=variant)
+        assert len(U) == U_ref.shape[1]
+        np.testing.assert_allclose(s, s_ref, rtol=1e-10)
+        assert O.subspace_angle(U_ref, U.to_numpy(), W) < 1e-8
+        assert O.orthogonality_error(U.to_numpy(), W) < 1e-10

@@ -43,6 +43,8 @@ timeout 300 python tools/bench_gs.py --dofs 10000000 --k 256 --variant bcgs2 --p
 grep -hE '^\{' gpurun_out/r02_gs_10Mx256_bcgs2.log | cut -c1-500
 grep -hE '^\{' gpurun_out/r02_gs_10Mx256_bcgs2_128_16.log | cut -c1-500
 grep -hE '^\{' gpurun_out/r02_gs_10Mx256_bcgs2_32_8.log | cut -c1-500
+timeout 600 python tools/bench_pod_qr.py > gpurun_out/r02_pod_qr_4Mx500.log 2>&1
+grep -hE '^\{' gpurun_out/r02_pod_qr_4Mx500.log | cut -c1-600
 timeout 300 python tools/bench_cholqr.py --dofs 10000000 --k 256 > gpurun_out/r02_cholqr_10Mx256.log 2>&1
 grep -hE '^\{' gpurun_out/r02_cholqr_10Mx256.log | cut -c1-400
 # HBM-bound kernels: 10M-DOF vectors, 12 columns -> a few hundred launches; capture a handful of each kind
