@@ -24,5 +24,8 @@ grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_bcgs2_128_16.log | cut -c1-500
 grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_bcgs2_32_8.log | cut -c1-500
 timeout 600 $TR tools/bench_cholqr.py --dofs 10000000 --k 256 > gpurun_out/r02_cholqr_${N}gpu.log 2>&1
 grep -hE '^\{' gpurun_out/r02_cholqr_${N}gpu.log | cut -c1-400
+# config 5 (Galerkin projection V^T (A V) of a 5-point CSR operator, halo exchange): 6.25M DOF x 2000 basis per GPU
+timeout 900 $TR tools/bench_project.py --nx 2500 --ny $((2500 * N)) --k 2000 --reps 2 > gpurun_out/r02_project_${N}gpu.log 2>&1
+grep -hE '^\{' gpurun_out/r02_project_${N}gpu.log | cut -c1-600
 timeout 1200 $TR bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r02_bench_${N}gpu.log 2>&1
 grep -hE '^\{' gpurun_out/r02_gs_${N}gpu_pairs.log gpurun_out/r02_gs_${N}gpu_sweep.log gpurun_out/r02_bench_${N}gpu.log | cut -c1-600
