@@ -7,7 +7,6 @@ sweep; a packet is never overwritten while somebody still has to read it (that w
 the exact-flag wait or as a wrong sum); two buffers per slot are enough, one is not.  The GPU parity of the
 kernel is tests/test_gpu_parity.py::test_mgs_sweep_parity (+ tests/sharded_worker.py for several GPUs).
 """
-import numpy as np
 import pytest
 
 
