@@ -346,3 +346,28 @@ def test_block_gram_schmidt_variant_vs_pymor_mgs(kind):
     for Q, R in ((Q1, R1), (Q2, R2), (Q3, R3), (Q4, R4)):
         np.testing.assert_allclose(Q.to_numpy(), Qn.to_numpy(), rtol=0, atol=1e-11)
         np.testing.assert_allclose(R, Rn, rtol=0, atol=1e-11)
+
+
+def test_numpy_conversion_operator_bridges_cpu_and_device():
+    """N4 bridging: pyMOR's own `NumpyConversionOperator` (operators/constructions.py:1384) works on
+    `CudaVectorSpace` as it is (`to_numpy` / `from_numpy`), so a CPU model can wrap a device operator --
+    `to_numpy o CudaCsrOperator o from_numpy` acts like the NumpyMatrixOperator of the same matrix -- and CPU
+    solves can feed device snapshot arrays."""
+    from pymor.operators.constructions import ConcatenationOperator, NumpyConversionOperator
+    dim = 97
+    M = (sps.random(dim, dim, density=0.08, random_state=4) + 2 * sps.eye(dim)).tocsr()
+    nsp, csp = NumpyVectorSpace(dim), CudaVectorSpace(dim, device=DEVICE)
+    up, down = NumpyConversionOperator(csp, 'from_numpy'), NumpyConversionOperator(csp, 'to_numpy')
+    assert up.source == nsp and up.range == csp and down.source == csp and down.range == nsp
+    wrapped = ConcatenationOperator([down, CudaCsrOperator(M, csp), up])
+    ref = NumpyMatrixOperator(M)
+    rng = np.random.default_rng(2)
+    U, V = nsp.from_numpy(rng.standard_normal((dim, 4))), nsp.from_numpy(rng.standard_normal((dim, 3)))
+    np.testing.assert_allclose(wrapped.apply(U).to_numpy(), ref.apply(U).to_numpy(), atol=1e-12)
+    np.testing.assert_allclose(wrapped.apply_adjoint(V).to_numpy(), ref.apply_adjoint(V).to_numpy(), atol=1e-12)
+    np.testing.assert_allclose(wrapped.apply2(V, U), ref.apply2(V, U), atol=1e-12)
+    snaps = csp.empty()
+    for i in range(len(U)):                                   # CPU "solves" appended to a device snapshot array
+        snaps.append(up.apply(U[i]))
+    assert isinstance(snaps, CudaVectorArray) and len(snaps) == 4
+    np.testing.assert_array_equal(snaps.to_numpy(), U.to_numpy())
