@@ -489,5 +489,20 @@ class Operator:
         assert len(U) == len(V)
         return V.pairwise_inner(self.apply(U, mu=mu))
 
+    solver = None
+
+    def apply_inverse(self, V, mu=None, initial_guess=None, return_info=False, solver=None):
+        """Dispatch to the operator's solver (operators/interface.py:174-208)."""
+        solver = solver or self.solver
+        if solver is None:
+            raise NotImplementedError('operator has no solver')
+        return solver.solve(self, V, mu=mu, initial_guess=initial_guess, return_info=return_info)
+
+    def apply_inverse_adjoint(self, U, mu=None, initial_guess=None, return_info=False, solver=None):
+        solver = solver or self.solver
+        if solver is None:
+            raise NotImplementedError('operator has no solver')
+        return solver.solve_adjoint(self, U, mu=mu, initial_guess=initial_guess, return_info=return_info)
+
     def assemble(self, mu=None):
         return self

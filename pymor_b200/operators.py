@@ -20,6 +20,7 @@ import torch
 
 from pymor_b200.complexarray import CudaComplexVectorArrayImpl
 from pymor_b200.interface import Operator
+from pymor_b200.solvers import CgSolver, DiagonalSolver
 from pymor_b200.vectorarray import CudaVectorArray, CudaVectorArrayImpl, CudaVectorSpace
 
 
@@ -48,11 +49,12 @@ class CudaDiagonalOperator(Operator):
 
     linear = True
 
-    def __init__(self, weights, space, name=None):
+    def __init__(self, weights, space, solver=None, name=None):
         assert isinstance(space, CudaVectorSpace)
         self.weights = weights
         self.space = space
         self.name = name
+        self.solver = solver if solver is not None else DiagonalSolver()     # apply_inverse: reciprocal weights
         self.source = self.range = space
         if isinstance(weights, torch.Tensor):
             w = weights.to(device=space.device, dtype=torch.float64).contiguous()
@@ -87,6 +89,15 @@ class CudaDiagonalOperator(Operator):
 
     def apply_adjoint(self, V, mu=None):
         return self.apply(V, mu=mu)
+
+    def inverse(self):
+        """The diagonal operator with the reciprocal weights (cached)."""
+        inv = self.__dict__.get('_inverse')
+        if inv is None:
+            inv = CudaDiagonalOperator(1.0 / self._w[:max(self.space.local_dim, 1)] if self.space.local_dim
+                                       else torch.zeros(0, dtype=torch.float64, device=self.space.device), self.space)
+            object.__setattr__(self, '_inverse', inv)
+        return inv
 
     def apply2(self, V, U, mu=None):
         assert V in self.range and U in self.source
@@ -185,14 +196,22 @@ class CudaCsrOperator(Operator):
 
     linear = True
 
-    def __init__(self, matrix, space, name=None):
+    def __init__(self, matrix, space, solver=None, name=None):
         assert isinstance(space, CudaVectorSpace)
         self.matrix = matrix
         self.space = space
         self.name = name
+        self.solver = solver
         self.source = self.range = space
         self._dev = None
         self._dev_T = None
+        if solver is None and matrix is not None and matrix.shape[0]:
+            # symmetric matrices (mass / stiffness / energy products) get conjugate gradients on the device, so that
+            # Riesz representatives `product.apply_inverse(residual)` stay there; others keep pyMOR's default
+            csr = sps.csr_matrix(matrix)
+            asym = abs(csr - csr.T)
+            if asym.nnz == 0 or asym.max() <= 1e-14 * abs(csr).max():
+                self.solver = CgSolver()
         if matrix is not None:
             assert matrix.shape == (space.dim, space.dim)
             self._dev = _ShardedCsr(sps.csr_matrix(matrix), space)
@@ -256,6 +275,18 @@ class CudaCsrOperator(Operator):
         assert V in self.range and U in self.source
         assert len(V) == len(U)
         return V.pairwise_inner(self.apply(U))
+
+    def jacobi_preconditioner(self):
+        """Inverse of the matrix diagonal as a :class:`CudaDiagonalOperator` (``None`` without the host matrix or
+        with a zero on the diagonal); cached."""
+        if '_jacobi' not in self.__dict__:
+            jac = None
+            if self.matrix is not None:
+                d = np.asarray(sps.csr_matrix(self.matrix).diagonal(), dtype=np.float64)
+                if d.size and np.all(d != 0):
+                    jac = CudaDiagonalOperator(1.0 / d, self.space)
+            object.__setattr__(self, '_jacobi', jac)
+        return self.__dict__['_jacobi']
 
     def assemble(self, mu=None):
         return self

@@ -371,3 +371,63 @@ def test_numpy_conversion_operator_bridges_cpu_and_device():
         snaps.append(up.apply(U[i]))
     assert isinstance(snaps, CudaVectorArray) and len(snaps) == 4
     np.testing.assert_array_equal(snaps.to_numpy(), U.to_numpy())
+
+
+def test_device_solvers_and_coercive_reductor_error_estimator_N4():
+    """`apply_inverse` on the CUDA operators (device CG / reciprocal weights through pyMOR's Solver interface) and,
+    built on it, pyMOR's `CoerciveRBReductor` with its residual-based error estimator on a DEVICE model: the Riesz
+    representatives `product.apply_inverse(residual)` (reductors/residual.py:151, algorithms/image.py:106) and
+    their Gram-Schmidt run on the device; estimates and errors agree with the all-NumPy pipeline."""
+    from pymor.analyticalproblems.thermalblock import thermal_block_problem
+    from pymor.discretizers.builtin import discretize_stationary_cg
+    from pymor.models.basic import StationaryModel
+    from pymor.parameters.functionals import ExpressionParameterFunctional
+    from pymor.reductors.coercive import CoerciveRBReductor
+
+    from pymor_b200.solvers import CgSolver, cg
+    # solvers on their own
+    dim = 200
+    K = sps.diags([-np.ones(dim - 1), 2.2 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1]).tocsr()
+    csp, nsp = CudaVectorSpace(dim, device=DEVICE), NumpyVectorSpace(dim)
+    op = CudaCsrOperator(K, csp)
+    assert isinstance(op.solver, CgSolver)
+    rng = np.random.default_rng(0)
+    Vh = rng.standard_normal((dim, 3))
+    V = csp.from_numpy(Vh)
+    assert np.abs(K @ op.apply_inverse(V).to_numpy() - Vh).max() < 1e-8
+    assert np.abs(K @ op.apply_inverse_adjoint(V).to_numpy() - Vh).max() < 1e-8
+    assert np.abs(K @ op.with_(solver=CgSolver(tol=1e-13)).apply_inverse(V).to_numpy() - Vh).max() < 1e-11
+    X, _ = cg(NumpyMatrixOperator(K).apply, nsp.from_numpy(Vh), tol=1e-13)      # interface-only: NumPy classes too
+    assert np.abs(K @ X.to_numpy() - Vh).max() < 1e-11
+    D = CudaDiagonalOperator(rng.uniform(0.5, 1.5, dim), csp)
+    assert np.abs(D.apply(D.apply_inverse(V)).to_numpy() - Vh).max() < 1e-14
+    assert CudaCsrOperator(K + sps.diags(np.ones(dim - 1), 1), csp).solver is None   # non-symmetric: pyMOR's default
+
+    # the reductor with error estimator
+    problem = thermal_block_problem(num_blocks=(2, 2))
+    fom, _ = discretize_stationary_cg(problem, diameter=1. / 10)
+    coercivity = ExpressionParameterFunctional('min(diffusion)', fom.parameters)
+    space = fom.parameters.space(0.1, 1.)
+    snaps = fom.solution_space.empty()
+    for mu in space.sample_uniformly(2):
+        snaps.append(fom.solve(mu))
+    csp = CudaVectorSpace(fom.solution_space.dim, device=DEVICE)
+    tight = CgSolver(tol=1e-13)
+    dev_ops = [CudaCsrOperator(o.matrix, csp) for o in fom.operator.operators]
+    dev_fom = StationaryModel(LincombOperator(dev_ops, fom.operator.coefficients),
+                              VectorOperator(csp.from_numpy(fom.rhs.as_range_array().to_numpy())))
+    dev_product = CudaCsrOperator(fom.h1_0_semi_product.matrix, csp, solver=tight)
+    rb_n, _ = pod(snaps, modes=5, product=fom.h1_0_semi_product)
+    rb_c, _ = pod(csp.from_numpy(snaps.to_numpy()), modes=5, product=dev_product)
+    rom_n = CoerciveRBReductor(fom, rb_n, product=fom.h1_0_semi_product, coercivity_estimator=coercivity).reduce()
+    red_c = CoerciveRBReductor(dev_fom, rb_c, product=dev_product, coercivity_estimator=coercivity)
+    rom_c = red_c.reduce()
+    assert isinstance(red_c.bases['RB'], CudaVectorArray)
+    for mu in space.sample_randomly(3):
+        u_n, u_c = rom_n.solve(mu), rom_c.solve(mu)
+        est_n, est_c = rom_n.estimate_error(mu), rom_c.estimate_error(mu)
+        np.testing.assert_allclose(est_c, est_n, rtol=1e-6)
+        U_fom = fom.solve(mu)
+        err_c = (red_c.reconstruct(u_c).to_numpy() - U_fom.to_numpy())
+        err_n = (rb_n.lincomb(u_n.to_numpy()).to_numpy() - U_fom.to_numpy())
+        np.testing.assert_allclose(np.linalg.norm(err_c), np.linalg.norm(err_n), rtol=1e-6)

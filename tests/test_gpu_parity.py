@@ -648,3 +648,22 @@ def test_mgs_sweep_parity(loaded_lib, rng):
         assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, None if gprod is None else g['w'], tight=1e-11)
         Q, R = alg.block_gram_schmidt(sp_g.from_numpy(g['A']), product=gprod, return_R=True, panel=4)
         assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, None if gprod is None else g['w'], tight=1e-11)
+
+
+@pytest.mark.skipif(os.environ.get('PMC_TEST_SWEEP') != '1', reason='late round-1 addition: runs on request')
+def test_device_cg_solver(loaded_lib, rng):
+    """apply_inverse of an SPD CSR operator by block conjugate gradients on the device (Riesz representatives of
+    the reductors' error estimators): 2-D 5-point Laplacian + mass shift, 40k DOFs, 6 right-hand sides."""
+    import scipy.sparse.linalg as spla
+
+    from pymor_b200.operators import CudaCsrOperator
+    nx = 200
+    T = sps.diags([-np.ones(nx - 1), 2.0 * np.ones(nx), -np.ones(nx - 1)], [-1, 0, 1])
+    K = (sps.kron(sps.eye(nx), T) + sps.kron(T, sps.eye(nx)) + 0.1 * sps.eye(nx * nx)).tocsr()
+    sp = space_of(nx * nx)
+    op = CudaCsrOperator(K, sp)
+    V = rng.standard_normal((nx * nx, 6))
+    U, info = op.apply_inverse(sp.from_numpy(V), return_info=True)
+    ref = spla.splu(K.tocsc()).solve(V)
+    assert info['iterations'] < 2000
+    np.testing.assert_allclose(U.to_numpy(), ref, atol=1e-8 * np.abs(ref).max())

@@ -727,3 +727,41 @@ def test_pod_qr_svd_with_block_gram_schmidt(emu, name):
         np.testing.assert_allclose(s, s_ref, rtol=1e-10)
         assert O.subspace_angle(U_ref, U.to_numpy(), W) < 1e-8
         assert O.orthogonality_error(U.to_numpy(), W) < 1e-10
+
+
+def test_device_solvers(emu, rng):
+    """apply_inverse on the CUDA operators: conjugate gradients on the whole block of right-hand sides (SpMM +
+    pairwise_inner + per-column axpy / scal), Jacobi-preconditioned, converged columns frozen; exact inverse for
+    diagonal operators; non-symmetric matrices get no default solver."""
+    import scipy.sparse.linalg as spla
+
+    from pymor_b200.operators import CudaCsrOperator, CudaDiagonalOperator
+    from pymor_b200.solvers import CgSolver, InversionError, cg
+    dim = 300
+    h = 1 / (dim + 1)
+    K = (sps.diags([-np.ones(dim - 1), 2.0 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1]) / h
+         + sps.diags(np.linspace(1, 3, dim))).tocsr()
+    sp = space_of(dim)
+    op = CudaCsrOperator(K, sp)
+    assert isinstance(op.solver, CgSolver)
+    V = rng.standard_normal((dim, 5))
+    V[:, 3] = 0                                               # a zero right-hand side converges at once
+    ref = spla.spsolve(K.tocsc(), V)
+    U, info = op.apply_inverse(sp.from_numpy(V), return_info=True)
+    assert 0 < info['iterations'] <= dim
+    np.testing.assert_allclose(U.to_numpy(), ref, atol=1e-9 * np.abs(ref).max())
+    assert np.all(U.to_numpy()[:, 3] == 0)
+    np.testing.assert_allclose(op.apply_inverse_adjoint(sp.from_numpy(V)).to_numpy(), ref, atol=1e-9 * np.abs(ref).max())
+    # warm start and explicit solver; without the preconditioner more iterations, same answer
+    U2, info2 = op.apply_inverse(sp.from_numpy(V), initial_guess=U, return_info=True, solver=CgSolver(tol=1e-10))
+    assert info2['iterations'] <= 2
+    U3, info3 = CgSolver(tol=1e-12, jacobi=False).solve(op, sp.from_numpy(V), return_info=True)
+    np.testing.assert_allclose(U3.to_numpy(), ref, atol=1e-9 * np.abs(ref).max())
+    w = rng.uniform(0.5, 1.5, dim)
+    D = CudaDiagonalOperator(w, sp)
+    np.testing.assert_allclose(D.apply_inverse(sp.from_numpy(V)).to_numpy(), V / w[:, None], rtol=1e-15)
+    assert CudaCsrOperator(K + sps.diags(np.ones(dim - 1), 1), sp).solver is None
+    with pytest.raises(InversionError):                       # indefinite operator: non-positive curvature
+        cg(CudaCsrOperator(sps.diags(np.where(np.arange(dim) % 2, 1.0, -1.0)).tocsr(), sp).apply, sp.from_numpy(V))
+    with pytest.raises(InversionError):
+        CgSolver(tol=1e-14, maxiter=3, jacobi=False).solve(op, sp.from_numpy(V))
