@@ -205,13 +205,7 @@ class CudaCsrOperator(Operator):
         self.source = self.range = space
         self._dev = None
         self._dev_T = None
-        if solver is None and matrix is not None and matrix.shape[0]:
-            # symmetric matrices (mass / stiffness / energy products) get conjugate gradients on the device, so that
-            # Riesz representatives `product.apply_inverse(residual)` stay there; others keep pyMOR's default
-            csr = sps.csr_matrix(matrix)
-            asym = abs(csr - csr.T)
-            if asym.nnz == 0 or asym.max() <= 1e-14 * abs(csr).max():
-                self.solver = CgSolver()
+
         if matrix is not None:
             assert matrix.shape == (space.dim, space.dim)
             self._dev = _ShardedCsr(sps.csr_matrix(matrix), space)
@@ -275,6 +269,29 @@ class CudaCsrOperator(Operator):
         assert V in self.range and U in self.source
         assert len(V) == len(U)
         return V.pairwise_inner(self.apply(U))
+
+    def default_solver(self):
+        """Solver used by ``apply_inverse`` when none was given: conjugate gradients on the device for symmetric
+        matrices (mass / stiffness / energy products -- Riesz representatives ``product.apply_inverse(residual)``
+        then stay on the device), ``None`` (pyMOR's default) otherwise.  Symmetry is checked on first use."""
+        if '_default_solver' not in self.__dict__:
+            sol = None
+            if self.matrix is not None and self.matrix.shape[0]:
+                csr = sps.csr_matrix(self.matrix)
+                asym = abs(csr - csr.T)
+                if asym.nnz == 0 or asym.max() <= 1e-14 * abs(csr).max():
+                    sol = CgSolver()
+            object.__setattr__(self, '_default_solver', sol)
+        return self.__dict__['_default_solver']
+
+    def apply_inverse(self, V, mu=None, initial_guess=None, return_info=False, solver=None):
+        solver = solver or self.solver or self.default_solver()
+        return super().apply_inverse(V, mu=mu, initial_guess=initial_guess, return_info=return_info, solver=solver)
+
+    def apply_inverse_adjoint(self, U, mu=None, initial_guess=None, return_info=False, solver=None):
+        solver = solver or self.solver or self.default_solver()
+        return super().apply_inverse_adjoint(U, mu=mu, initial_guess=initial_guess, return_info=return_info,
+                                             solver=solver)
 
     def jacobi_preconditioner(self):
         """Inverse of the matrix diagonal as a :class:`CudaDiagonalOperator` (``None`` without the host matrix or

@@ -390,7 +390,7 @@ def test_device_solvers_and_coercive_reductor_error_estimator_N4():
     K = sps.diags([-np.ones(dim - 1), 2.2 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1]).tocsr()
     csp, nsp = CudaVectorSpace(dim, device=DEVICE), NumpyVectorSpace(dim)
     op = CudaCsrOperator(K, csp)
-    assert isinstance(op.solver, CgSolver)
+    assert op.solver is None and isinstance(op.default_solver(), CgSolver)
     rng = np.random.default_rng(0)
     Vh = rng.standard_normal((dim, 3))
     V = csp.from_numpy(Vh)
@@ -401,7 +401,7 @@ def test_device_solvers_and_coercive_reductor_error_estimator_N4():
     assert np.abs(K @ X.to_numpy() - Vh).max() < 1e-11
     D = CudaDiagonalOperator(rng.uniform(0.5, 1.5, dim), csp)
     assert np.abs(D.apply(D.apply_inverse(V)).to_numpy() - Vh).max() < 1e-14
-    assert CudaCsrOperator(K + sps.diags(np.ones(dim - 1), 1), csp).solver is None   # non-symmetric: pyMOR's default
+    assert CudaCsrOperator(K + sps.diags(np.ones(dim - 1), 1), csp).default_solver() is None   # pyMOR's default
 
     # the reductor with error estimator
     problem = thermal_block_problem(num_blocks=(2, 2))

@@ -743,7 +743,7 @@ def test_device_solvers(emu, rng):
          + sps.diags(np.linspace(1, 3, dim))).tocsr()
     sp = space_of(dim)
     op = CudaCsrOperator(K, sp)
-    assert isinstance(op.solver, CgSolver)
+    assert op.solver is None and isinstance(op.default_solver(), CgSolver)
     V = rng.standard_normal((dim, 5))
     V[:, 3] = 0                                               # a zero right-hand side converges at once
     ref = spla.spsolve(K.tocsc(), V)
@@ -760,7 +760,7 @@ def test_device_solvers(emu, rng):
     w = rng.uniform(0.5, 1.5, dim)
     D = CudaDiagonalOperator(w, sp)
     np.testing.assert_allclose(D.apply_inverse(sp.from_numpy(V)).to_numpy(), V / w[:, None], rtol=1e-15)
-    assert CudaCsrOperator(K + sps.diags(np.ones(dim - 1), 1), sp).solver is None
+    assert CudaCsrOperator(K + sps.diags(np.ones(dim - 1), 1), sp).default_solver() is None
     with pytest.raises(InversionError):                       # indefinite operator: non-positive curvature
         cg(CudaCsrOperator(sps.diags(np.where(np.arange(dim) % 2, 1.0, -1.0)).tocsr(), sp).apply, sp.from_numpy(V))
     with pytest.raises(InversionError):
