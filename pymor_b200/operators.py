@@ -270,6 +270,30 @@ class CudaCsrOperator(Operator):
         assert len(V) == len(U)
         return V.pairwise_inner(self.apply(U))
 
+    def _assemble_lincomb(self, operators, coefficients, identity_shift=0., name=None):
+        """pyMOR's hook for ``LincombOperator.assemble`` (reference counterpart: operators/numpy.py:243-287): a real
+        linear combination of CSR / diagonal device operators on this space with host matrices becomes ONE
+        ``CudaCsrOperator`` (assembled with SciPy on the host, uploaded once), so that ``fom.solve(mu)`` of a device
+        model is a single device solve instead of a chain of operator applications."""
+        mats = []
+        for op in operators:
+            if isinstance(op, CudaCsrOperator) and op.matrix is not None and op.space == self.space:
+                mats.append(sps.csr_matrix(op.matrix))
+            elif isinstance(op, CudaDiagonalOperator) and op.space == self.space and not isinstance(op.weights, torch.Tensor):
+                mats.append(sps.diags(np.asarray(op.weights, dtype=np.float64).reshape(-1)).tocsr())
+            else:
+                return None
+        coeffs = list(coefficients) + [identity_shift]
+        if any(np.iscomplexobj(c) and np.imag(c) != 0 for c in coeffs):
+            return None
+        total = None
+        for m, c in zip(mats, coefficients):
+            term = m * float(np.real(c))
+            total = term if total is None else total + term
+        if identity_shift != 0:
+            total = total + sps.eye(total.shape[0]) * float(np.real(identity_shift))
+        return CudaCsrOperator(total.tocsr(), self.space, solver=self.solver, name=name)
+
     def default_solver(self):
         """Solver used by ``apply_inverse`` when none was given: conjugate gradients on the device for symmetric
         matrices (mass / stiffness / energy products -- Riesz representatives ``product.apply_inverse(residual)``
