@@ -90,6 +90,10 @@ class CudaDiagonalOperator(Operator):
     def apply_adjoint(self, V, mu=None):
         return self.apply(V, mu=mu)
 
+    def _assemble_lincomb(self, operators, coefficients, identity_shift=0., name=None):
+        """See :meth:`CudaCsrOperator._assemble_lincomb` (this operator may be the first of the combination)."""
+        return CudaCsrOperator._assemble_lincomb(self, operators, coefficients, identity_shift=identity_shift, name=name)
+
     def inverse(self):
         """The diagonal operator with the reciprocal weights (cached)."""
         inv = self.__dict__.get('_inverse')
@@ -292,7 +296,8 @@ class CudaCsrOperator(Operator):
             total = term if total is None else total + term
         if identity_shift != 0:
             total = total + sps.eye(total.shape[0]) * float(np.real(identity_shift))
-        return CudaCsrOperator(total.tocsr(), self.space, solver=self.solver, name=name)
+        solver = self.solver if isinstance(self, CudaCsrOperator) else None
+        return CudaCsrOperator(total.tocsr(), self.space, solver=solver, name=name)
 
     def default_solver(self):
         """Solver used by ``apply_inverse`` when none was given: conjugate gradients on the device for symmetric
