@@ -475,3 +475,16 @@ def test_device_model_solve_and_rb_greedy_N4():
         sorted(sorted(m.to_numpy().tolist()) for m in g_n['max_err_mus'])
     np.testing.assert_allclose(g_c['max_errs'], g_n['max_errs'], rtol=1e-5)
     assert isinstance(red_c.bases['RB'], CudaVectorArray) and len(red_c.bases['RB']) == len(red_n.bases['RB']) == 4
+
+
+@pytest.mark.parametrize('kind', ['euclid', 'diag'])
+def test_gram_schmidt_biorth_runs_unchanged(kind):
+    """The biorthogonal variant in the same reference file (gram_schmidt.py:125-222) uses the same primitives."""
+    from pymor.algorithms.gram_schmidt import gram_schmidt_biorth
+    A, nsp, csp, nprod, cprod = make(120, 7, 5, kind)
+    B = np.asfortranarray(A + 0.3 * np.random.default_rng(6).standard_normal(A.shape))
+    Vn, Wn = gram_schmidt_biorth(nsp.from_numpy(A.copy()), nsp.from_numpy(B.copy()), product=nprod)
+    Vc, Wc = gram_schmidt_biorth(csp.from_numpy(A), csp.from_numpy(B), product=cprod)
+    np.testing.assert_allclose(Vc.to_numpy(), Vn.to_numpy(), atol=1e-10)
+    np.testing.assert_allclose(Wc.to_numpy(), Wn.to_numpy(), atol=1e-10)
+    np.testing.assert_allclose(Wc.inner(Vc, cprod), np.eye(7), atol=1e-12)
