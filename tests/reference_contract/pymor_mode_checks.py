@@ -488,3 +488,39 @@ def test_gram_schmidt_biorth_runs_unchanged(kind):
     np.testing.assert_allclose(Vc.to_numpy(), Vn.to_numpy(), atol=1e-10)
     np.testing.assert_allclose(Wc.to_numpy(), Wn.to_numpy(), atol=1e-10)
     np.testing.assert_allclose(Wc.inner(Vc, cprod), np.eye(7), atol=1e-12)
+
+
+def test_more_reference_algorithms_run_unchanged():
+    """Other pyMOR algorithms that only touch the backend through the VectorArray / Operator interface: the
+    implicitly restarted Arnoldi eigensolver (`algorithms/eigs.py`), dynamic mode decomposition (`algorithms/dmd.py`,
+    built on the SVD of svd_va.py) and the block Arnoldi process with `E^{-1}` (`algorithms/krylov.py:12`, device
+    solver behind `apply_inverse`)."""
+    from pymor.algorithms.dmd import dmd
+    from pymor.algorithms.eigs import eigs
+    from pymor.algorithms.krylov import arnoldi
+    from pymor.tools.random import new_rng
+    dim = 150
+    K = sps.diags([-np.ones(dim - 1), 2.2 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1]).tocsr()
+    w = np.linspace(1, 2, dim)
+    nsp, csp = NumpyVectorSpace(dim), CudaVectorSpace(dim, device=DEVICE)
+    with new_rng(0):
+        ew_n, _ = eigs(NumpyMatrixOperator(K), k=3, which='LM')
+    with new_rng(0):
+        ew_c, ev_c = eigs(CudaCsrOperator(K, csp), k=3, which='LM')
+    np.testing.assert_allclose(np.sort(ew_c.real), np.sort(ew_n.real), rtol=1e-8)
+    assert isinstance(ev_c, CudaVectorArray)
+    rng = np.random.default_rng(1)
+    Aop = rng.standard_normal((dim, dim)) / np.sqrt(dim)
+    X = np.zeros((dim, 12))
+    X[:, 0] = rng.standard_normal(dim)
+    for i in range(1, 12):
+        X[:, i] = Aop @ X[:, i - 1]
+    _, om_n = dmd(nsp.from_numpy(X), modes=5)
+    _, om_c = dmd(csp.from_numpy(X), modes=5)
+    np.testing.assert_allclose(np.sort_complex(om_c), np.sort_complex(om_n), rtol=1e-7)
+    b = rng.standard_normal((dim, 1))
+    Vn = arnoldi(NumpyMatrixOperator(K), NumpyMatrixOperator(sps.diags(w).tocsr()), nsp.from_numpy(b), 5)
+    Vc = arnoldi(CudaCsrOperator(K, csp), CudaDiagonalOperator(w, csp), csp.from_numpy(b), 5)
+    assert isinstance(Vc, CudaVectorArray) and len(Vc) == len(Vn)
+    G = nsp.from_numpy(Vc.to_numpy()).inner(Vn)
+    np.testing.assert_allclose(np.abs(np.linalg.svd(G, compute_uv=False)), 1.0, atol=1e-6)
