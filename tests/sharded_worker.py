@@ -139,6 +139,11 @@ def main():
         np.testing.assert_allclose(op.apply2(VV, UU), V.T @ (M @ U), atol=1e-11)
         np.testing.assert_allclose(op.pairwise_apply2(VV, UU[:kv]), O.pairwise_inner(V, U[:, :kv], M), atol=1e-11)
         np.testing.assert_allclose(alg.project(op, VV, UU, product=prod), O.project(M, V, U, P), atol=1e-11)
+        if not real or os.environ.get('PMC_TEST_SWEEP') == '1':
+            # block CG with the halo-exchanging SpMM: Riesz representatives on row-sharded arrays
+            import scipy.sparse.linalg as spla
+            X = prod.apply_inverse(UU)
+            np.testing.assert_allclose(X.to_numpy(), spla.spsolve(P.tocsc(), U), atol=1e-8 * np.abs(U).max() * 6)
         if dim >= ku:
             Q, R = alg.gram_schmidt(UU, product=prod, return_R=True)
             Qo, Ro = O.gram_schmidt(U, P, return_R=True)
