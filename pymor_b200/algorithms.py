@@ -14,8 +14,8 @@ touch raw data, like their reference counterparts):
 * :func:`shifted_chol_qr`       -- src/pymor/algorithms/chol_qr.py:16-252 ("next" row N1: the GEMM-bound
   orthonormalisation -- three Gramians + three block lincombs instead of k^2 dot/axpy pairs with a
   host sync each, i.e. the variant that scales over DOF-sharded GPUs)
-* :func:`inc_vectorarray_hapod`, :func:`dist_vectorarray_hapod` -- src/pymor/algorithms/hapod.py:333, :372
-  ("next" row N3)
+* :func:`inc_vectorarray_hapod`, :func:`dist_vectorarray_hapod`, :func:`inc_hapod_chunks` (snapshots streamed
+  from host memory chunk by chunk) -- src/pymor/algorithms/hapod.py:333, :372 ("next" row N3)
 * :func:`randomized_range_finder` -- src/pymor/algorithms/rand_la.py:20 ("next" row N2, fixed-size mode)
 * :func:`block_gram_schmidt` (= ``gram_schmidt(variant='bcgs2')``) and ``gram_schmidt(variant='cgs2')`` -- not in
   the reference: the classical / block-classical Gram-Schmidt variants with re-orthogonalisation that turn the
@@ -539,6 +539,36 @@ def shifted_chol_qr(A, product=None, return_R=False, maxiter=3, offset=0, orth_t
     R[:offset, offset:] = Bi
     R[offset:, offset:] = Ri
     return A, R
+
+
+def inc_hapod_chunks(chunks, steps, eps, omega, product=None):
+    """Incremental HAPOD over snapshot chunks that arrive one at a time (``chunks``: an iterable of ``steps``
+    |VectorArrays|, e.g. ``space.from_local_numpy(host_block)`` per block of a snapshot set that does not fit into
+    HBM next to its modes; each chunk is consumed -- emptied -- by the node it feeds).  Same chain tree and local
+    tolerances as :func:`inc_vectorarray_hapod` (src/pymor/algorithms/hapod.py:333-370, :414-424); only one chunk
+    and the carried modes are resident at any time.  Returns ``modes, svals, snap_count``."""
+    levels = int(steps)
+    carried, snap_count = None, 0
+    modes = svals = None
+    idx = -1
+    for idx, node in enumerate(chunks):
+        assert idx < levels, 'more chunks than announced steps'
+        snap_count += len(node)
+        if carried is not None:
+            node.append(carried, remove_from_other=True)
+        is_root = idx == levels - 1
+        if is_root:
+            tol = np.sqrt(snap_count) * omega * eps
+        else:
+            tol = np.sqrt(snap_count) / np.sqrt(levels - 1) * np.sqrt(1 - omega ** 2) * eps
+        modes, svals = pod(node, product=product, atol=0., rtol=0., l2_err=tol,
+                           orth_tol=1e-10 if is_root else np.inf)
+        del node[:]
+        if not is_root:
+            modes.scal(svals)
+            carried = modes
+    assert idx == levels - 1, 'fewer chunks than announced steps'
+    return modes, svals, snap_count
 
 
 def inc_vectorarray_hapod(steps, U, eps, omega, product=None):

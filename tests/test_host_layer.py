@@ -482,6 +482,27 @@ def test_standalone_inc_hapod_golden(emu, name):
         assert O.orthogonality_error(modes.to_numpy(), W) < 1e-10
 
 
+def test_inc_hapod_over_host_chunks(emu):
+    """inc_hapod_chunks: the snapshots arrive chunk by chunk from host memory (a set too large for HBM); identical
+    to inc_vectorarray_hapod on the resident array."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    g = load_golden('hapod')
+    A, w = g['A'], g['w']
+    sp = space_of(A.shape[0])
+    prod = CudaDiagonalOperator(w, sp)
+    steps = 4
+    chunk = -(-A.shape[1] // steps)
+    blocks = (sp.from_local_numpy(np.asfortranarray(A[:, s:s + chunk])) for s in range(0, A.shape[1], chunk))
+    modes, svals, count = alg.inc_hapod_chunks(blocks, steps, 1e-3, 0.75, product=prod)
+    ref_modes, ref_svals, ref_count = alg.inc_vectorarray_hapod(steps, sp.from_numpy(A), 1e-3, 0.75, product=prod)
+    assert count == ref_count == A.shape[1] and len(modes) == len(ref_modes)
+    np.testing.assert_array_equal(svals, ref_svals)
+    np.testing.assert_array_equal(modes.to_numpy(), ref_modes.to_numpy())
+    np.testing.assert_allclose(svals, g[f'svals_diag_{steps}'], rtol=1e-8)
+    with pytest.raises(AssertionError):
+        alg.inc_hapod_chunks((sp.from_numpy(A[:, :5]) for _ in range(2)), 3, 1e-3, 0.75)
+
+
 @pytest.mark.parametrize('name', ['euclid', 'diag'])
 def test_standalone_dist_hapod_golden(emu, name):
     """N3, distributed tree: two-level (one POD per slice + root) and a binary tree over 7 slices."""
