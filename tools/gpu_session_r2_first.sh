@@ -27,7 +27,7 @@ unset PMC_TEST_GRAM2
 # fused Gram-Schmidt sweep (csrc/mgs.cu): gated parity test under a short timeout (the kernel's waits give up
 # after 5 s on their own), then config 3 pair-by-pair vs swept
 PMC_TEST_SWEEP=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 --timeout-method thread \
-    -k mgs_sweep > gpurun_out/r02_pytest_sweep.log 2>&1
+    -k "mgs_sweep or device_cg" > gpurun_out/r02_pytest_sweep.log 2>&1
 echo "pytest sweep exit $?" >> gpurun_out/r02_pytest_sweep.log
 tail -n 4 gpurun_out/r02_pytest_sweep.log
 if grep -q "pytest sweep exit 0" gpurun_out/r02_pytest_sweep.log; then
