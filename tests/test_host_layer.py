@@ -786,3 +786,26 @@ def test_device_solvers(emu, rng):
         cg(CudaCsrOperator(sps.diags(np.where(np.arange(dim) % 2, 1.0, -1.0)).tocsr(), sp).apply, sp.from_numpy(V))
     with pytest.raises(InversionError):
         CgSolver(tol=1e-14, maxiter=3, jacobi=False).solve(op, sp.from_numpy(V))
+
+
+def test_block_variants_keep_orthogonality_on_ill_conditioned_input(emu, rng):
+    """"Orthogonality error no worse than the reference's" (north star): on inputs of condition 1e2 ... 1e13 the
+    classical (cgs2) and block (bcgs2) variants with re-orthogonalisation stay at O(eps) like the reference's
+    re-iterated MGS, and A = Q R holds to rounding."""
+    from pymor_b200.operators import CudaDiagonalOperator
+    dim, k = 600, 40
+    sp = space_of(dim)
+    prod = CudaDiagonalOperator(rng.uniform(0.5, 1.5, dim), sp)
+    for cond in (1e2, 1e8, 1e13):
+        U, _ = np.linalg.qr(rng.standard_normal((dim, k)))
+        V, _ = np.linalg.qr(rng.standard_normal((k, k)))
+        A = U @ np.diag(np.logspace(0, -np.log10(cond), k)) @ V.T
+        ref_Q = alg.gram_schmidt(sp.from_numpy(A), product=prod)
+        ref = np.abs(ref_Q.gramian(prod) - np.eye(len(ref_Q))).max()
+        for kw in (dict(variant='cgs2'), dict(variant='bcgs2'), dict(variant='mgs', sweep=True)):
+            Q, R = alg.gram_schmidt(sp.from_numpy(A), product=prod, return_R=True, **kw)
+            assert len(Q) == len(ref_Q) == k
+            assert np.abs(Q.gramian(prod) - np.eye(k)).max() <= max(4 * ref, 5e-15), (cond, kw)
+            np.testing.assert_allclose(Q.to_numpy() @ R, A, atol=1e-14)
+        Q, R = alg.block_gram_schmidt(sp.from_numpy(A), product=prod, return_R=True, panel=(16, 4))
+        assert np.abs(Q.gramian(prod) - np.eye(k)).max() <= max(4 * ref, 5e-15)
