@@ -237,12 +237,14 @@ def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, 
     def project(cols, against):
         """cols -= Q (Q^T W cols) for Q = A[against]; returns the coefficients (len(against), len(cols))."""
         X = view(cols)
-        WX = weigh(X)
+        # products that weigh inside the Gramian kernel (diagonal weights on the device) skip the temporary W X
+        fused = product is not None and getattr(product, 'fused_apply2', False)
+        WX = X if fused else weigh(X)
         S = np.zeros((len(against), len(cols)))
         row = 0
         for start, count in _column_runs(against):
             Q = A[start:start + count]
-            C = Q.inner(WX)
+            C = product.apply2(Q, X) if fused else Q.inner(WX)
             X.axpy(-1., Q.lincomb(C))
             S[row:row + count] = C
             row += count

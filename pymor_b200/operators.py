@@ -48,6 +48,7 @@ class CudaDiagonalOperator(Operator):
     """
 
     linear = True
+    fused_apply2 = True        # apply2 / pairwise_apply2 weigh inside the reduction kernels: no temporary W U
 
     def __init__(self, weights, space, solver=None, name=None):
         assert isinstance(space, CudaVectorSpace)
