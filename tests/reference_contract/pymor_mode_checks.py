@@ -524,3 +524,38 @@ def test_more_reference_algorithms_run_unchanged():
     assert isinstance(Vc, CudaVectorArray) and len(Vc) == len(Vn)
     G = nsp.from_numpy(Vc.to_numpy()).inner(Vn)
     np.testing.assert_allclose(np.abs(np.linalg.svd(G, compute_uv=False)), 1.0, atol=1e-6)
+
+
+def test_accelerate_pymor_routes_device_arrays_to_block_gram_schmidt():
+    """`pymor_b200.accelerate.accelerate_pymor()`: an unchanged pyMOR program -- `pod` with its default `qr_svd`
+    method, `extend_basis` of a reductor -- runs its Gram-Schmidt through the block variant when the arrays are
+    device arrays, and through pyMOR's own function otherwise; `restore_pymor()` undoes the patch."""
+    import pymor.algorithms.gram_schmidt as gs_mod
+    import pymor.algorithms.pod as pod_mod
+    import pymor.algorithms.svd_va as svd_mod
+
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.accelerate import accelerate_pymor, restore_pymor
+    A, nsp, csp, nprod, cprod = make(157, 12, 1, 'diag')
+    original = gs_mod.gram_schmidt
+    calls = []
+    real_bgs = alg.block_gram_schmidt
+
+    def spy(*a, **kw):
+        calls.append('bcgs2')
+        return real_bgs(*a, **kw)
+    alg.block_gram_schmidt = spy
+    try:
+        accelerate_pymor('bcgs2')
+        assert svd_mod.gram_schmidt is not original and pod_mod.gram_schmidt is svd_mod.gram_schmidt
+        Un, sn = pod(nsp.from_numpy(A.copy()), product=nprod)                 # NumPy arrays: pyMOR's own path
+        assert not calls
+        Uc, sc = pod_mod.pod(csp.from_numpy(A), product=cprod)                # default method qr_svd -> block GS
+        assert calls and isinstance(Uc, CudaVectorArray)
+        np.testing.assert_allclose(sc, sn, rtol=1e-10)
+        G = nsp.from_numpy(Uc.to_numpy()).inner(Un, nprod)
+        np.testing.assert_allclose(np.abs(np.linalg.svd(G, compute_uv=False)), 1.0, atol=1e-8)
+    finally:
+        restore_pymor()
+        alg.block_gram_schmidt = real_bgs
+    assert svd_mod.gram_schmidt is original and gs_mod.gram_schmidt is original
