@@ -19,7 +19,8 @@
 //  * the diagonal weight is applied ONCE per stage in shared memory (each warp scales 1/16 of the B tile
 //    three stages ahead: 4 DMUL per warp and stage) instead of on every warp's fragments (16 DMUL per
 //    warp and stage).  For diagonal tiles the scaled copy goes to the B slot the tile does not load.
-//    Products round exactly as in gram_dmma_kernel (fl(w*b) first), so unsplit blocks are bitwise equal.
+//    Products round exactly as in gram_dmma_kernel (fl(w*b) first), so blocks whose K range is not split are
+//    bitwise equal (bit 64 of gram_opts disables all K-splits).
 //
 // The index maps live in gram2_plan.h and are checked on the CPU by tests/native/gram2_model.cpp.
 #include "common.cuh"
