@@ -1,28 +1,26 @@
-"""Stand-alone drivers of the hot-path algorithms.
+"""Extensions of pyMOR's hot-path algorithms for device-resident arrays.
 
-These are the CALLERS of the backend.  With pyMOR installed use pyMOR's own functions -- they run
-unchanged on :class:`~pymor_b200.vectorarray.CudaVectorArray`.  On a box without pyMOR (the GPU box of
-this project) the functions below provide the same algorithms with the same names, arguments,
-defaults and error behaviour, written against the VectorArray/Operator interface only (they never
-touch raw data, like their reference counterparts):
+pyMOR's own functions are the callers of this backend and run on :class:`~pymor_b200.vectorarray.CudaVectorArray`
+unchanged; this module re-exports them under their reference names so that `pymor_b200.algorithms.<name>` IS the
+reference function (no restatement):
 
-* :func:`gram_schmidt`          -- src/pymor/algorithms/gram_schmidt.py:13-122
-* :func:`method_of_snapshots`   -- src/pymor/algorithms/svd_va.py:20-99
-* :func:`qr_svd`                -- src/pymor/algorithms/svd_va.py:103-168
-* :func:`pod`                   -- src/pymor/algorithms/pod.py:16-90
-* :func:`project`               -- src/pymor/algorithms/projection.py:28-85 (rule ``action_apply_basis``)
-* :func:`shifted_chol_qr`       -- src/pymor/algorithms/chol_qr.py:16-252 ("next" row N1: the GEMM-bound
-  orthonormalisation -- three Gramians + three block lincombs instead of k^2 dot/axpy pairs with a
-  host sync each, i.e. the variant that scales over DOF-sharded GPUs)
-* :func:`inc_vectorarray_hapod`, :func:`dist_vectorarray_hapod`, :func:`inc_hapod_chunks` (snapshots streamed
-  from host memory chunk by chunk) -- src/pymor/algorithms/hapod.py:333, :372 ("next" row N3)
-* :func:`randomized_range_finder` -- src/pymor/algorithms/rand_la.py:20 ("next" row N2, fixed-size mode)
-* :func:`block_gram_schmidt` (= ``gram_schmidt(variant='bcgs2')``) and ``gram_schmidt(variant='cgs2')`` -- not in
-  the reference: the classical / block-classical Gram-Schmidt variants with re-orthogonalisation that turn the
-  O(k^2) host-synchronised pair-steps of gram_schmidt.py:84-91 into O(k) streaming resp. tensor-core calls; same
-  contract and (the QR factorisation being unique) the same results to rounding x conditioning
-* :func:`ei_greedy`, :func:`deim` -- src/pymor/algorithms/ei.py:30, :182 ("next" row N5: empirical
-  interpolation data; the backend sees ``amax`` / ``dofs`` / per-column ``axpy`` / ``norm`` / ``lincomb``)
+* :func:`method_of_snapshots`   -- pymor.algorithms.svd_va (src/pymor/algorithms/svd_va.py:20-99)
+* :func:`project`               -- pymor.algorithms.projection (src/pymor/algorithms/projection.py:28-85)
+* :func:`shifted_chol_qr`       -- pymor.algorithms.chol_qr (src/pymor/algorithms/chol_qr.py:16-252; "next" row N1)
+* :func:`inc_vectorarray_hapod`, :func:`dist_vectorarray_hapod` -- pymor.algorithms.hapod (:333, :372; N3)
+* :func:`ei_greedy`, :func:`deim` -- pymor.algorithms.ei (:30, :182; N5)
+* ``RandomizedRangeFinder`` / ``randomized_svd`` -- pymor.algorithms.rand_la (:20, :378; N2)
+
+What is defined HERE is what the reference does not have:
+
+* :func:`gram_schmidt` -- pyMOR's ``gram_schmidt`` (src/pymor/algorithms/gram_schmidt.py:13-122; called directly for
+  ``variant='mgs'`` without ``sweep``) plus ``sweep=True`` (one fused device kernel per pass instead of one launch
+  and one host synchronisation per pair) and ``variant='cgs2'`` / ``'bcgs2'`` (:func:`block_gram_schmidt`): the
+  classical / block-classical Gram-Schmidt variants with re-orthogonalisation that turn the O(k^2)
+  host-synchronised pair-steps of gram_schmidt.py:84-91 into O(k) streaming resp. tensor-core calls; same contract
+  and (the QR factorisation being unique) the same results to rounding x conditioning
+* :func:`qr_svd` / :func:`pod` -- pyMOR's functions, with the option to run the QR step with one of those variants
+* :func:`inc_hapod_chunks` -- incremental HAPOD over snapshot chunks streamed from host memory
 """
 from __future__ import annotations
 
@@ -32,12 +30,22 @@ import os
 import numpy as np
 import scipy.linalg as spla
 
+from pymor_b200 import interface as _interface  # noqa: F401  (puts pyMOR on sys.path)
+from pymor.algorithms import gram_schmidt as _ref_gs  # noqa: E402
+from pymor.algorithms import pod as _ref_pod  # noqa: E402
+from pymor.algorithms import svd_va as _ref_svd_va  # noqa: E402
+from pymor.algorithms.chol_qr import shifted_chol_qr  # noqa: E402,F401
+from pymor.algorithms.ei import deim, ei_greedy  # noqa: E402,F401
+from pymor.algorithms.hapod import dist_vectorarray_hapod, inc_vectorarray_hapod  # noqa: E402,F401
+from pymor.algorithms.projection import project  # noqa: E402,F401
+from pymor.algorithms.rand_la import RandomizedRangeFinder, randomized_svd  # noqa: E402,F401
+from pymor.algorithms.svd_va import method_of_snapshots  # noqa: E402,F401
+from pymor.core.exceptions import AccuracyError  # noqa: E402,F401
+
+# pyMOR's own function, also while accelerate_pymor() has the module attribute point to its dispatcher
+_pymor_gram_schmidt = getattr(_ref_gs.gram_schmidt, '__wrapped__', _ref_gs.gram_schmidt)
+
 logger = logging.getLogger('pymor_b200.algorithms')
-
-
-class AccuracyError(Exception):
-    """Raised when the result of :func:`gram_schmidt` fails the orthonormality check."""
-
 
 def _sweep_weight(A, product):
     """Device address of the diagonal weight (0: Euclidean) if the inner loop of :func:`gram_schmidt` can
@@ -78,6 +86,12 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
     ``'bcgs2'``: :func:`block_gram_schmidt` (panels of vectors against all previous ones through the tensor-core
     Gramian / lincomb kernels)."""
     assert variant in ('mgs', 'cgs2', 'bcgs2')
+    if sweep is None:
+        sweep = os.environ.get('PMC_MGS_SWEEP', '0') == '1'
+    if variant == 'mgs' and not sweep:
+        return _pymor_gram_schmidt(A, product=product, return_R=return_R, atol=atol, rtol=rtol, offset=offset,
+                                    reiterate=reiterate, reiteration_threshold=reiteration_threshold, check=check,
+                                    check_tol=check_tol, copy=copy)
     if variant == 'bcgs2':
         return block_gram_schmidt(A, product=product, return_R=return_R, atol=atol, rtol=rtol, offset=offset,
                                   reiteration_threshold=reiteration_threshold, check=check, check_tol=check_tol,
@@ -87,9 +101,11 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
     k = len(A)
     R = np.eye(k)
     dropped = []
-    if sweep is None:
-        sweep = os.environ.get('PMC_MGS_SWEEP', '0') == '1'
     weight_ptr = _sweep_weight(A, product) if sweep else None
+    if weight_ptr is not None:
+        # the sweeps write through the raw impl: un-share it first (copy() above is lazy, and with copy=False other
+        # arrays may hold lazy copies of A) -- what VectorArray-level writes do via _copy_impl_if_multiple_refs
+        A._copy_impl_if_multiple_refs()
     Z = None                # weighted sweeps: panel of the pre-weighted final columns w * q_j (same positions as in A)
     if weight_ptr:
         from pymor_b200.vectorarray import CudaVectorArrayImpl
@@ -189,6 +205,15 @@ def gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, offset
     return (A, R) if return_R else A
 
 
+def _holds_complex(A):
+    """Whether the array stores complex data (device arrays: a pair of real panels; NumPy arrays: the dtype)."""
+    impl = getattr(A, 'impl', None)
+    if type(impl).__name__ == 'CudaComplexVectorArrayImpl':
+        return True
+    arr = getattr(impl, '_array', None)
+    return arr is not None and np.iscomplexobj(arr)
+
+
 def _column_runs(cols):
     """Maximal runs of consecutive integers in the sorted list ``cols`` as ``(start, count)``: each run is a
     zero-copy slice view of the array."""
@@ -223,6 +248,12 @@ def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, 
     with the norm of the input vector)."""
     panels = tuple(int(b) for b in (panel if isinstance(panel, (tuple, list)) else (panel,)))
     assert 0 <= offset <= len(A) and all(b >= 1 for b in panels)
+    if _holds_complex(A):
+        # the host factors S / F / R below are real; complex data (a contract-completeness path, not a performance
+        # path: DESIGN.md §8) takes the classical variant, which promotes R on the first complex coefficient
+        return gram_schmidt(A, product=product, return_R=return_R, atol=atol, rtol=rtol, offset=offset,
+                            reiteration_threshold=reiteration_threshold, check=check, check_tol=check_tol, copy=copy,
+                            variant='cgs2', sweep=False)
     if copy:
         A = A.copy()
     k = len(A)
@@ -352,62 +383,35 @@ def block_gram_schmidt(A, product=None, return_R=False, atol=1e-13, rtol=1e-13, 
     return (A, R) if return_R else A
 
 
-def _select_modes(s, modes, rtol, atol, l2_err):
-    above = np.nonzero(s >= max(rtol * s[0], atol))[0]
-    if above.size == 0:
-        return 0
-    tail_energy = np.concatenate((np.cumsum(s[::-1] ** 2)[::-1], [0.]))
-    n_err = int(np.nonzero(tail_energy <= l2_err ** 2)[0][0])
-    count = min(n_err, int(above[-1]) + 1)
-    return count if modes is None else min(count, modes)
-
-
-def method_of_snapshots(A, product=None, modes=None, rtol=1e-7, atol=0., l2_err=0.):
-    """SVD of ``A`` through the eigendecomposition of its (weighted) Gramian.  Returns
-    ``U`` (VectorArray of left singular vectors), ``s``, ``Vh``.  The small eigenproblem stays on
-    the host (LAPACK ``dsyevr`` via SciPy)."""
-    if A.dim == 0 or len(A) == 0:
-        return A.space.empty(), np.array([]), np.zeros((0, len(A)))
-    k = len(A)
-    G = A.gramian(product)
-    window = None if (modes is None or l2_err > 0.) else (max(k - modes, 0), k - 1)
-    evals, V = spla.eigh(G, overwrite_a=True, subset_by_index=window)
-    evals, V = evals[::-1], V[:, ::-1]
-    s = np.sqrt(np.clip(evals, a_min=0., a_max=None))
-    m = _select_modes(s, modes, rtol, atol, l2_err)
-    if m > A.dim:
-        logger.warning('Number of computed singular vectors larger than array dimension! Truncating ...')
-        m = A.dim
-    s, V = s[:m], V[:, :m]
-    return A.lincomb(V / s), s, V.conj().T
-
-
 def qr_svd(A, product=None, modes=None, rtol=4e-8, atol=0., l2_err=0., gs_variant='mgs'):
-    """SVD of ``A`` through Gram-Schmidt QR and the SVD of the small ``R`` factor.
+    """SVD of ``A`` through Gram-Schmidt QR and the SVD of the small ``R`` factor: pyMOR's ``qr_svd``
+    (src/pymor/algorithms/svd_va.py:103-168), called directly for ``gs_variant='mgs'``.
 
     ``gs_variant`` (not in the reference): the Gram-Schmidt variant of :func:`gram_schmidt` used for the QR step.
     ``'bcgs2'`` runs it on the tensor cores (~4 n k^2 flop, O(k) host syncs) instead of k(k-1) host-synchronised
     pair-steps -- the POD that does NOT square the condition number then costs about as much as the method of
     snapshots."""
+    if gs_variant == 'mgs':
+        return _ref_svd_va.qr_svd(A, product=product, modes=modes, rtol=rtol, atol=atol, l2_err=l2_err)
     if A.dim == 0 or len(A) == 0:
         return A.space.empty(), np.array([]), np.zeros((0, len(A)))
     Q, R = gram_schmidt(A, product=product, return_R=True, check=False, variant=gs_variant)
     U2, s, Vh = spla.svd(R, lapack_driver='gesvd')
-    m = _select_modes(s, modes, rtol, atol, l2_err)
+    m = _ref_svd_va._select_modes(s, modes, rtol, atol, l2_err)
     return Q.lincomb(U2[:, :m]), s[:m], Vh[:m]
-
-
-SVD_VA_METHODS = {'method_of_snapshots': method_of_snapshots, 'qr_svd': qr_svd}
 
 
 def pod(A, product=None, modes=None, rtol=1e-7, atol=0., l2_err=0., method='qr_svd', orth_tol=1e-10,
         return_reduced_coefficients=False, **method_options):
-    """Proper orthogonal decomposition of ``A``; re-orthonormalises the modes with
-    :func:`gram_schmidt` when their orthogonality error is not below ``orth_tol``.  ``method_options`` (not in
-    the reference) are handed to the SVD method, e.g. ``method='qr_svd', gs_variant='bcgs2'``."""
-    assert method in SVD_VA_METHODS
-    modes_va, svals, coeffs = SVD_VA_METHODS[method](A, product=product, modes=modes, rtol=rtol, atol=atol,
-                                                     l2_err=l2_err, **method_options)
+    """pyMOR's ``pod`` (src/pymor/algorithms/pod.py:16-90), called directly unless ``method_options`` (not in the
+    reference) are given: those are handed to the SVD method, e.g. ``method='qr_svd', gs_variant='bcgs2'``, and the
+    orthonormality check / re-orthonormalisation of pod.py:78-86 follows as in the reference."""
+    if not method_options:
+        return _ref_pod.pod(A, product=product, modes=modes, rtol=rtol, atol=atol, l2_err=l2_err, method=method,
+                            orth_tol=orth_tol, return_reduced_coefficients=return_reduced_coefficients)
+    svd = {'method_of_snapshots': method_of_snapshots, 'qr_svd': qr_svd}[method]
+    modes_va, svals, coeffs = svd(A, product=product, modes=modes, rtol=rtol, atol=atol, l2_err=l2_err,
+                                  **method_options)
     if modes_va.dim > 0 and len(modes_va) > 0 and np.isfinite(orth_tol):
         err = np.max(np.abs(modes_va.inner(modes_va, product) - np.eye(len(modes_va))))
         if err >= orth_tol:
@@ -416,131 +420,6 @@ def pod(A, product=None, modes=None, rtol=1e-7, atol=0., l2_err=0., method='qr_s
     if return_reduced_coefficients:
         return modes_va, svals, coeffs
     return modes_va, svals
-
-
-def project(op, range_basis, source_basis, product=None):
-    """Petrov-Galerkin projection of a linear, non-parametric operator.
-
-    Returns the projected matrix ``(len(range_basis), len(source_basis))`` as a NumPy array when both
-    bases are given (pyMOR wraps the same array in a ``NumpyMatrixOperator``); with only one basis the
-    VectorArray ``op.apply_adjoint(range_basis)`` resp. ``op.apply(source_basis)`` is returned."""
-    assert source_basis is None or source_basis in op.source
-    assert range_basis is None or range_basis in op.range
-    assert product is None or product.source == product.range == op.range
-    if range_basis is None and source_basis is None:
-        return op
-    rb = product.apply(range_basis) if (product is not None and range_basis is not None) else range_basis
-    if source_basis is None:
-        return op.apply_adjoint(rb)
-    if rb is None:
-        return op.apply(source_basis)
-    return op.apply2(rb, source_basis)
-
-
-def _product_norm_estimate(product, iters=20):
-    """Spectral norm of an SPD product operator by power iteration (the reference calls
-    ``pymor.algorithms.eigs.eigs(product, k=1)``, chol_qr.py:185-187; any estimate of the same
-    quantity serves: it only scales the diagonal shift)."""
-    v = product.source.random(1, distribution='normal')
-    lam = 1.0
-    for _ in range(iters):
-        v.scal(1.0 / v.norm()[0])
-        v = product.apply(v)
-        lam = v.norm()[0]
-    return float(lam)
-
-
-class _ShiftedCholesky:
-    """Cholesky factor of a Gramian, shifted on breakdown (chol_qr.py:171-252)."""
-    INNER_ITERS = 10
-
-    def __init__(self, dim, product, product_norm, check_finite, recompute):
-        self.dim, self.product, self.product_norm = dim, product, product_norm
-        self.check_finite, self.recompute, self.shift = check_finite, recompute, None
-
-    def _compute_shift(self, X):
-        m, n = self.dim, len(X)
-        eps = np.finfo(X.dtype).eps
-        shift = 11 * eps
-        if self.product is None:
-            shift *= m * n + n * (n + 1)
-        else:
-            if self.product_norm is None:
-                self.product_norm = np.sqrt(_product_norm_estimate(self.product))
-            shift *= (2 * m * np.sqrt(m * n) + n * (n + 1)) * self.product_norm
-        top = spla.eigh(X, eigvals_only=True, subset_by_index=[n - 1, n - 1], driver='evr')[0]
-        return max(shift * top, eps)
-
-    def apply(self, X):
-        shift = 0.0
-        for it in range(self.INNER_ITERS):
-            try:
-                M = X + np.eye(len(X)) * shift if self.recompute else X
-                return spla.cholesky(M, overwrite_a=False, check_finite=self.check_finite)
-            except spla.LinAlgError:
-                logger.warning('Cholesky factorization broke down! Matrix is ill-conditioned.')
-                if self.recompute:
-                    shift = self._compute_shift(X) if it == 0 else shift * 10
-                else:
-                    if not self.shift:
-                        self.shift = self._compute_shift(X)
-                    X[np.diag_indices_from(X)] += self.shift
-        raise AccuracyError('Failed to compute a Cholesky factorization of X.')
-
-
-def shifted_chol_qr(A, product=None, return_R=False, maxiter=3, offset=0, orth_tol=None,
-                    recompute_shift=False, check_finite=True, copy=True, product_norm=None):
-    """Shifted CholeskyQR(3): Gramian -> Cholesky (diagonally shifted on breakdown) -> block
-    lincomb with the inverse factor, repeated ``maxiter`` times.  Same arguments and behaviour as the
-    reference; all n-sized work is GEMM-class (``inner``/``gramian``/``lincomb``/``append``)."""
-    assert 0 <= offset <= len(A)
-    assert A.dim >= len(A)
-    assert 0 < maxiter
-    assert orth_tol is None or 0 < orth_tol
-    if copy:
-        A = A.copy()
-    k = len(A)
-    if offset == k:
-        return (A, np.eye(k)) if return_R else A
-    chol = _ShiftedCholesky(A.dim, product, product_norm, check_finite, recompute_shift)
-
-    def gram_blocks():
-        G = A.inner(A[offset:], product=product)
-        return G[:offset].astype(np.float64, copy=False), G[offset:].astype(np.float64, copy=False)
-
-    B, X = gram_blocks()
-    Bi = Ri = None
-    it = 1
-    while it <= maxiter:
-        X = X - B.conj().T @ B
-        Rx = chol.apply(X)
-        Rinv = spla.solve_triangular(Rx, np.eye(len(Rx)), lower=False, check_finite=check_finite)
-        todo = A[:offset].lincomb(-B @ Rinv) + A[offset:].lincomb(Rinv)
-        del A[offset:]
-        A.append(todo)
-        if it == 1:
-            Bi, Ri = B, Rx
-        else:
-            Bi = Bi + B @ Ri
-            Ri = Rx @ Ri
-        if it < maxiter:
-            B, X = gram_blocks()
-        elif orth_tol is not None:
-            X = A[offset:].gramian(product=product)
-        if orth_tol is not None:
-            res = spla.norm(X - np.eye(k - offset), ord='fro', check_finite=check_finite)
-            if res <= orth_tol * np.sqrt(k):
-                break
-            if it == maxiter:
-                raise AccuracyError('Orthonormality could not be achieved within the given tolerance. '
-                                    'Consider increasing maxiter or enabling recompute_shift.')
-        it += 1
-    if not return_R:
-        return A
-    R = np.eye(k)
-    R[:offset, offset:] = Bi
-    R[offset:, offset:] = Ri
-    return A, R
 
 
 def inc_hapod_chunks(chunks, steps, eps, omega, product=None):
@@ -571,204 +450,3 @@ def inc_hapod_chunks(chunks, steps, eps, omega, product=None):
             carried = modes
     assert idx == levels - 1, 'fewer chunks than announced steps'
     return modes, svals, snap_count
-
-
-def inc_vectorarray_hapod(steps, U, eps, omega, product=None):
-    """Incremental hierarchical approximate POD ("next" row N3; reference:
-    src/pymor/algorithms/hapod.py:333-370 over the chain tree of :95-104 with the local tolerances of
-    :414-424): the snapshots are consumed in ``steps`` chunks, each intermediate node is one
-    :func:`pod` of [new chunk, previous modes scaled by their singular values].  Returns
-    ``modes, svals, snap_count``.  Lets POD run on snapshot sets that do not fit HBM at once."""
-    chunk = -(-len(U) // steps)
-    starts = list(range(0, len(U), chunk))
-    levels = len(starts)                       # tree depth - 1 (no POD on the leaves)
-    carried, snap_count = None, 0
-    modes = svals = None
-    for idx, s in enumerate(starts):
-        node = U[s:s + chunk].copy()
-        snap_count += len(node)
-        if carried is not None:
-            node.append(carried, remove_from_other=True)
-        is_root = idx == levels - 1
-        if is_root:
-            tol = np.sqrt(snap_count) * omega * eps
-        else:
-            tol = np.sqrt(snap_count) / np.sqrt(levels - 1) * np.sqrt(1 - omega ** 2) * eps
-        modes, svals = pod(node, product=product, atol=0., rtol=0., l2_err=tol,
-                           orth_tol=1e-10 if is_root else np.inf)
-        if not is_root:
-            modes.scal(svals)
-            carried = modes
-    return modes, svals, snap_count
-
-
-def dist_vectorarray_hapod(num_slices, U, eps, omega, arity=None, product=None):
-    """Distributed hierarchical approximate POD ("next" row N3; reference:
-    src/pymor/algorithms/hapod.py:372-410 over the tree of :106-126 with the local tolerances of :414-424):
-    the snapshots are cut into ``num_slices`` slices, every leaf is the :func:`pod` of one slice, every inner
-    node the :func:`pod` of its children's modes scaled by their singular values; ``arity=None`` gives the
-    two-level tree (one POD per slice, one of the collected modes).  Returns ``modes, svals, snap_count``.
-    The nodes run one after the other on the device (the reference's ``executor`` only adds host threads)."""
-    chunk = -(-len(U) // num_slices)
-    starts = list(range(0, len(U), chunk))
-    fan = len(starts) if arity is None else arity
-
-    def build(slices):                         # nested lists; an int is a leaf (slice number)
-        if len(slices) > fan:
-            return [build(list(part)) if len(part) > 1 else int(part[0]) for part in np.array_split(slices, fan)]
-        return [int(i) for i in slices]
-
-    def depth(node):
-        return 1 if isinstance(node, int) else 1 + max(depth(c) for c in node)
-
-    tree = build(list(range(len(starts))))
-    levels = depth(tree)
-
-    def local_pod(V, snap_count, is_root):
-        if is_root:
-            tol = np.sqrt(snap_count) * omega * eps
-        else:
-            tol = np.sqrt(snap_count) / np.sqrt(levels - 1) * np.sqrt(1 - omega ** 2) * eps
-        return pod(V, product=product, atol=0., rtol=0., l2_err=tol, orth_tol=1e-10 if is_root else np.inf)
-
-    def visit(node, is_root):
-        if isinstance(node, int):
-            V = U[starts[node]:starts[node] + chunk].copy()
-            count = len(V)
-        else:
-            V, count = None, 0
-            for child in node:
-                modes, svals, c = visit(child, False)
-                modes.scal(svals)
-                count += c
-                if V is None:
-                    V = modes
-                else:
-                    V.append(modes, remove_from_other=True)
-        modes, svals = local_pod(V, count, is_root)
-        return modes, svals, count
-
-    return visit(tree, True)
-
-
-def randomized_range_finder(A, basis_size, power_iterations=0, range_product=None, qr_method='gram_schmidt'):
-    """Orthonormal basis of the (approximate) range of the operator ``A`` from ``basis_size`` random
-    samples ("next" row N2; reference: src/pymor/algorithms/rand_la.py:20-252, fixed-size mode):
-    ``Q = orth(A Omega)``, then ``power_iterations`` times ``Q = orth(A A^T Q)``.  Uses only
-    ``Operator.apply`` / ``apply_adjoint``, ``space.random`` and the orthonormalisation."""
-    def orth(V):
-        if qr_method == 'shifted_chol_qr':
-            return shifted_chol_qr(V, product=range_product, copy=False)
-        return gram_schmidt(V, product=range_product, atol=0., rtol=0., copy=False)
-
-    Q = orth(A.apply(A.source.random(basis_size, distribution='normal')))
-    for _ in range(power_iterations):
-        Q = orth(A.apply(A.apply_adjoint(Q)))
-    return Q
-
-
-def ei_greedy(U, error_norm=None, atol=None, rtol=None, max_interpolation_dofs=None, nodal_basis=False,
-              copy=True):
-    """Interpolation DOFs and collateral basis by the EI-greedy search ("next" row N5; reference:
-    src/pymor/algorithms/ei.py:30-179, sequential branch).  In every round the worst approximated
-    vector becomes a basis vector, normalised to 1 at its largest entry (the new interpolation DOF),
-    and is eliminated from all vectors at that DOF.  Per round the backend runs one ``amax``, two
-    ``dofs``, one ``axpy`` with per-column coefficients over the whole array (24 n k bytes) and one
-    ``norm`` / ``sup_norm`` (8 n k bytes): HBM-bound, one host sync per reduction.
-
-    ``error_norm``: ``None`` (Euclidean), ``'sup'`` or a callable ``VectorArray -> ndarray``.
-    Returns ``interpolation_dofs, collateral_basis, data`` with the reference's ``data`` keys."""
-    assert not isinstance(error_norm, str) or error_norm == 'sup'
-    assert len(U) > 0
-    if error_norm is None:
-        def measure(V):
-            return V.norm()
-    elif error_norm == 'sup':
-        def measure(V):
-            return V.sup_norm()
-    else:
-        measure = error_norm
-    k = len(U)
-    dofs = np.zeros((0,), dtype=np.int32)
-    basis = U.space.empty()
-    K = np.eye(k)                                  # U_current = U_initial.lincomb(K)
-    coefficients = np.zeros((k, 0))
-    max_errs = []
-    if copy:
-        U = U.copy()
-    errs = measure(U)
-    worst = int(np.argmax(errs))
-    first_err = err = errs[worst]
-    while True:
-        if max_interpolation_dofs is not None and len(dofs) >= max_interpolation_dofs:
-            logger.info('Maximum number of interpolation DOFs reached (error %g)', err)
-            break
-        if atol is not None and err <= atol:
-            break
-        if rtol is not None and err / first_err <= rtol:
-            break
-        vec = U[worst].copy()
-        dof = vec.amax()[0][0]
-        if dof in dofs:
-            logger.info('DOF %d selected twice for interpolation, stopping', dof)
-            break
-        pivot = vec.dofs([dof])[0, 0]
-        if pivot == 0.:
-            logger.info('DOF %d selected for interpolation has zero maximum error, stopping', dof)
-            break
-        vec.scal(1 / pivot)
-        dofs = np.hstack((dofs, dof))
-        basis.append(vec)
-        coefficients = np.hstack([coefficients, K[:, worst:worst + 1] / pivot])
-        max_errs.append(err)
-        row = U.dofs([dof])
-        U.axpy(-row[0, :], vec)
-        K -= K[:, worst:worst + 1] @ (row / pivot)
-        errs = measure(U)
-        worst = int(np.argmax(errs))
-        err = errs[worst]
-    matrix = basis.dofs(dofs)
-    tri = np.abs(matrix - np.tril(matrix))
-    tri_errs = [np.max(tri[:d, :d]) for d in range(1, len(matrix) + 1)]
-    if nodal_basis:
-        inv = spla.inv(matrix)
-        basis = basis.lincomb(inv)
-        coefficients = coefficients @ inv
-        matrix = np.eye(len(basis))
-    return dofs, basis, {'errors': max_errs, 'triangularity_errors': tri_errs, 'coefficients': coefficients,
-                         'interpolation_matrix': matrix}
-
-
-def deim(U, modes=None, pod=True, atol=None, rtol=None, product=None, pod_options={}):
-    """Interpolation DOFs and collateral basis by DEIM ("next" row N5; reference:
-    src/pymor/algorithms/ei.py:182-264): POD of ``U`` (unless ``pod=False``), then for every mode the
-    DOF where its interpolation residual w.r.t. the previous modes is largest.  Returns
-    ``interpolation_dofs, collateral_basis, data`` (``data['svals']`` when the POD ran)."""
-    data = {}
-    if pod:
-        kw = dict(pod_options)
-        if atol is not None:
-            kw['atol'] = atol
-        if rtol is not None:
-            kw['rtol'] = rtol
-        basis, svals = globals()['pod'](U, modes=modes, product=product, **kw)
-        data['svals'] = svals
-    else:
-        basis = U
-    dofs = np.zeros((0,), dtype=np.int32)
-    matrix = np.zeros((0, 0))
-    for i in range(len(basis)):
-        if len(dofs) > 0:
-            coeff = spla.solve(matrix, basis[i].dofs(dofs))
-            resid = basis[i] - basis[:len(dofs)].lincomb(coeff)
-        else:
-            resid = basis[i]
-        dof = resid.amax()[0][0]
-        if dof in dofs:
-            logger.info('DOF %d selected twice for interpolation, stopping', dof)
-            break
-        dofs = np.hstack((dofs, dof))
-        matrix = basis[:len(dofs)].dofs(dofs)
-    if len(dofs) < len(basis):
-        del basis[len(dofs):len(basis)]
-    return dofs, basis, data

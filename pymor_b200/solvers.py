@@ -13,8 +13,8 @@ one of the backend's kernels:
   preconditioner.  Converged columns are frozen (coefficient 0).
 * :class:`DiagonalSolver` -- exact inverse of a :class:`~pymor_b200.operators.CudaDiagonalOperator`.
 
-With pyMOR importable both are ``pymor.solvers.interface.Solver`` subclasses (usable as ``op.with_(solver=...)``
-or ``apply_inverse(..., solver=...)``); without pyMOR they expose the same ``solve`` / ``solve_adjoint`` calls.
+Both are ``pymor.solvers.interface.Solver`` subclasses (usable as ``op.with_(solver=...)`` or
+``apply_inverse(..., solver=...)``).
 They use nothing but the interface, so they also run on pyMOR's NumPy classes (that is how they are checked
 against SciPy on the CPU).
 """
@@ -22,31 +22,9 @@ from __future__ import annotations
 
 import numpy as np
 
-try:  # pragma: no cover - depends on the environment
-    from pymor.core.exceptions import InversionError
-    from pymor.solvers.interface import Solver as _SolverBase
-    _HAVE_PYMOR = True
-except Exception:
-    _HAVE_PYMOR = False
-
-    class InversionError(Exception):
-        """Raised when a linear solve does not converge (mirror of pymor.core.exceptions.InversionError)."""
-
-    class _SolverBase:
-        """Stand-alone mirror of ``pymor.solvers.interface.Solver``: ``solve`` / ``solve_adjoint`` front ends."""
-
-        least_squares = False
-
-        def solve(self, operator, V, mu=None, initial_guess=None, return_info=False):
-            assert V in operator.range
-            assert initial_guess is None or (initial_guess in operator.source and len(initial_guess) == len(V))
-            result = self._solve(operator, V, mu=mu, initial_guess=initial_guess)
-            return result if return_info else result[0]
-
-        def solve_adjoint(self, operator, U, mu=None, initial_guess=None, return_info=False):
-            assert U in operator.source
-            result = self._solve_adjoint(operator, U, mu=mu, initial_guess=initial_guess)
-            return result if return_info else result[0]
+from pymor_b200 import interface as _interface  # noqa: F401  (puts pyMOR on sys.path)
+from pymor.core.exceptions import InversionError  # noqa: E402
+from pymor.solvers.interface import Solver as _SolverBase  # noqa: E402
 
 
 def cg(apply, V, tol=1e-10, maxiter=None, preconditioner=None, initial_guess=None):
@@ -112,8 +90,7 @@ class CgSolver(_SolverBase):
 
     def __init__(self, tol=1e-10, maxiter=None, jacobi=True):
         self.tol, self.maxiter, self.jacobi = tol, maxiter, jacobi
-        if _HAVE_PYMOR:                     # ImmutableObject: lock after construction like __auto_init would
-            self.__auto_init(locals())
+        self.__auto_init(locals())       # ImmutableObject: stores the arguments and locks the instance
 
     def _solve(self, operator, V, mu, initial_guess):
         op = operator.assemble(mu)
@@ -132,8 +109,7 @@ class DiagonalSolver(_SolverBase):
     """Exact inverse of a diagonal operator: multiply by the reciprocal weights."""
 
     def __init__(self):
-        if _HAVE_PYMOR:
-            self.__auto_init(locals())
+        self.__auto_init(locals())
 
     def _solve(self, operator, V, mu, initial_guess):
         return operator.assemble(mu).inverse().apply(V), {}

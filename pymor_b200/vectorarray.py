@@ -26,7 +26,7 @@ import torch
 from pymor_b200 import _lib
 from pymor_b200._lib import PMC_FORCE_SIMPLE, PMC_SYMMETRIC, PMC_SYNC
 from pymor_b200.dist import SingleRank, merge_amax, partition
-from pymor_b200.interface import HAVE_PYMOR, VectorArray, VectorArrayImpl, VectorSpace, create_random_values
+from pymor_b200.interface import VectorArray, VectorArrayImpl, VectorSpace, create_random_values
 
 _ALIGN = 16  # doubles
 _FLOAT_TYPES = (float, np.float64, int)

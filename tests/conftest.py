@@ -4,9 +4,9 @@ Markers
 -------
 gpu : needs a real B200 (run with ``-m gpu``); everything else runs on CPU (``-m "not gpu"``).
 
-The reference (pyMOR) is importable only in the build container (``/root/reference``); tests that
-drive the reference live are skipped when it is absent, the committed fixtures in ``tests/golden``
-stand in for it.
+pyMOR is the host library of the product; it is imported from ``baseline/_ref`` (the unmodified reference tree
+that ``__graft_entry__.build()`` places there; it travels to the GPU box).  Tests marked ``reference`` additionally
+need the reference's own test-suite (``src/pymortests``) from that tree.
 """
 import os
 import sys
@@ -19,14 +19,19 @@ ROOT = Path(__file__).resolve().parents[1]
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
-REFERENCE_SRC = Path('/root/reference/src')
-HAVE_REFERENCE = (REFERENCE_SRC / 'pymor' / '__init__.py').exists()
+from pymor_b200.interface import reference_root  # noqa: E402
+
+# the reference tree (pyMOR + its own test-suite): baseline/_ref, placed by __graft_entry__.build() and shipped to
+# the GPU box; /root/reference itself exists only in the build container and is never read by a -m gpu test
+REFERENCE_ROOT = reference_root()
+HAVE_REFERENCE = REFERENCE_ROOT is not None and (REFERENCE_ROOT / 'src' / 'pymortests' / 'vectorarray.py').exists()
+REFERENCE_SRC = REFERENCE_ROOT / 'src' if HAVE_REFERENCE else Path('/root/reference/src')
 GOLDEN = ROOT / 'tests' / 'golden'
 
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: test needs a CUDA device (B200)')
-    config.addinivalue_line('markers', 'reference: test imports the reference from /root/reference')
+    config.addinivalue_line('markers', 'reference: test runs the reference test-suite (baseline/_ref/src/pymortests)')
 
 
 def pytest_collection_modifyitems(config, items):
@@ -36,7 +41,7 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         have_gpu = False
     skip_gpu = pytest.mark.skip(reason='no CUDA device')
-    skip_ref = pytest.mark.skip(reason='/root/reference not present')
+    skip_ref = pytest.mark.skip(reason='reference tree (baseline/_ref) not present')
     for item in items:
         if 'gpu' in item.keywords and not have_gpu:
             item.add_marker(skip_gpu)

@@ -1,6 +1,6 @@
 """Run the REFERENCE's own pytest/hypothesis contract suite against the CUDA backend's host layer.
 
-Build-container only (needs /root/reference).  The reference parametrises its VectorArray tests over
+Needs the reference tree (baseline/_ref, placed by __graft_entry__.build(); else /root/reference).  The reference parametrises its VectorArray tests over
 backend names looked up in ``pymortests.strategies`` (src/pymortests/strategies.py:110-184); external
 backends register by adding a ``_<name>_vector_spaces`` factory.  We register ``'cuda'`` from here
 (the reference tree is read-only and stays untouched) and hand over to pytest; hypothesis draws
@@ -16,10 +16,13 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[2]
-REF = Path('/root/reference')
-sys.path.insert(0, str(REF / 'src'))
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / 'tests'))
+from pymor_b200.interface import reference_root  # noqa: E402
+
+REF = reference_root()            # baseline/_ref (placed by __graft_entry__.build(), travels to the GPU box)
+assert REF is not None, 'the contract suite needs the reference tree (src/pymortests): run __graft_entry__.build()'
+sys.path.insert(0, str(REF / 'src'))
 
 import numpy as np  # noqa: E402
 from hypothesis import strategies as hyst  # noqa: E402

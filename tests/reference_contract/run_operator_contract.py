@@ -1,7 +1,7 @@
 """Run the REFERENCE's Operator contract tests (src/pymortests/operators/operators.py) on the CUDA
 operators (CudaDiagonalOperator, CudaCsrOperator and pyMOR constructions built from them).
 
-Build-container only (needs /root/reference).  The reference parametrises these tests over generator
+Needs the reference tree (baseline/_ref, placed by __graft_entry__.build(); else /root/reference).  The reference parametrises these tests over generator
 lists in ``pymortests.fixtures.operator`` that are frozen into the fixtures at import; external backends
 (FEniCS, dolfinx) append their generators there (fixtures/operator.py:617-627, :766-768).  The reference
 tree is read-only, so the same registration is applied from outside: the two fixtures are re-created
@@ -14,10 +14,13 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[2]
-REF = Path('/root/reference')
-sys.path.insert(0, str(REF / 'src'))
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / 'tests'))
+from pymor_b200.interface import reference_root  # noqa: E402
+
+REF = reference_root()            # baseline/_ref (placed by __graft_entry__.build(), travels to the GPU box)
+assert REF is not None, 'the contract suite needs the reference tree (src/pymortests): run __graft_entry__.build()'
+sys.path.insert(0, str(REF / 'src'))
 
 import numpy as np  # noqa: E402
 import pytest  # noqa: E402

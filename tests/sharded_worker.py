@@ -120,7 +120,7 @@ def main():
                       + sps.eye(int(d)) for i, d in enumerate(dims)]
             M = sps.block_diag(blocks).tocsr()
             op = CudaCsrOperator(M, sp)
-            np.testing.assert_allclose(alg.project(op, VA, VB), O.project(M, A, B), atol=1e-11)
+            np.testing.assert_allclose(alg.project(op, VA, VB).matrix, O.project(M, A, B), atol=1e-11)
     # CSR operators coupling rows of different shards: halo exchange of the boundary rows
     # (what the reference delegates to "MPI-aware operators", src/pymor/operators/mpi.py:22-26)
     for dim in (7, 64, 301):
@@ -138,7 +138,7 @@ def main():
         np.testing.assert_allclose(op.apply_adjoint(VV).to_numpy(), M.T @ V, atol=1e-12)
         np.testing.assert_allclose(op.apply2(VV, UU), V.T @ (M @ U), atol=1e-11)
         np.testing.assert_allclose(op.pairwise_apply2(VV, UU[:kv]), O.pairwise_inner(V, U[:, :kv], M), atol=1e-11)
-        np.testing.assert_allclose(alg.project(op, VV, UU, product=prod), O.project(M, V, U, P), atol=1e-11)
+        np.testing.assert_allclose(alg.project(op, VV, UU, product=prod).matrix, O.project(M, V, U, P), atol=1e-11)
         if not real or os.environ.get('PMC_TEST_SWEEP') == '1':
             # block CG with the halo-exchanging SpMM: Riesz representatives on row-sharded arrays
             import scipy.sparse.linalg as spla

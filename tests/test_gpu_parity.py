@@ -312,11 +312,11 @@ def test_projection_and_thermalblock_golden(loaded_lib):
     sp = space_of(g['V'].shape[0])
     op, prod = CudaCsrOperator(csr_from(g, 'Mop'), sp), CudaCsrOperator(csr_from(g, 'P'), sp)
     V, U = sp.from_numpy(g['V']), sp.from_numpy(g['U'])
-    np.testing.assert_allclose(alg.project(op, V, U), g['proj_both'], rtol=1e-12, atol=1e-12)
-    np.testing.assert_allclose(alg.project(op, V, U, product=prod), g['proj_both_product'], rtol=1e-12, atol=1e-12)
-    np.testing.assert_allclose(alg.project(op, U, U), g['proj_galerkin'], rtol=1e-12, atol=1e-12)
-    np.testing.assert_allclose(alg.project(op, None, U).to_numpy(), g['proj_source_only'], rtol=1e-12, atol=1e-12)
-    np.testing.assert_allclose(alg.project(op, V, None).inner(U), g['proj_range_only'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, V, U).matrix, g['proj_both'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, V, U, product=prod).matrix, g['proj_both_product'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, U, U).matrix, g['proj_galerkin'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, None, U).array.to_numpy(), g['proj_source_only'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alg.project(op, V, None).array.inner(U), g['proj_range_only'], rtol=1e-12, atol=1e-12)
     t = load_golden('thermalblock')
     S, P = t['snapshots'], csr_from(t, 'P')
     sp = space_of(S.shape[0])
@@ -330,7 +330,7 @@ def test_projection_and_thermalblock_golden(loaded_lib):
     for i in range(int(t['n_ops'])):
         n = len(t[f'op{i}_indptr']) - 1
         Mi = sps.csr_matrix((t[f'op{i}_data'], t[f'op{i}_indices'], t[f'op{i}_indptr']), shape=(n, n))
-        np.testing.assert_allclose(alg.project(CudaCsrOperator(Mi, sp), B, B), t[f'op{i}_proj'], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(alg.project(CudaCsrOperator(Mi, sp), B, B).matrix, t[f'op{i}_proj'], rtol=1e-12, atol=1e-12)
 
 
 def test_csr_twoform_multi_panel(loaded_lib, rng):
@@ -543,7 +543,7 @@ def test_next_rows_hapod_and_range_finder(loaded_lib, rng):
     Mfull = sps.coo_matrix((B.ravel(), (rr.ravel(), cc.ravel())), shape=(dim, dim)).tocsr()
     sp = space_of(dim)
     op = CudaCsrOperator(Mfull, sp)
-    Q = alg.randomized_range_finder(op, 10, power_iterations=1)
+    Q = alg.RandomizedRangeFinder(op, power_iterations=1, error_estimator='loo').find_range(basis_size=10)
     Qh = Q.to_numpy()
     assert O.orthogonality_error(Qh) < 1e-10
     resid = L - Qh @ (Qh.T @ L)
