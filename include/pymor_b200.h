@@ -47,6 +47,9 @@ typedef enum {
 #define PMC_SYNC 1u        /* synchronise the stream before returning (results visible on host) */
 #define PMC_SYMMETRIC 2u   /* pmc_gram: B is the same panel as A -> SYRK (lower tiles + mirror)  */
 #define PMC_FORCE_SIMPLE 4u /* use the generic DFMA kernel even where the TMA/DMMA path applies (tests) */
+#define PMC_LOWER_ONLY 8u  /* pmc_gram / pmc_csr_gram: the caller knows the (square) result is symmetric although the two
+                              operands differ (V^T (M V) with symmetric M): contract only the tiles on/below the diagonal
+                              and mirror -- half the flop */
 
 typedef struct pmc_ctx pmc_ctx;
 
@@ -69,6 +72,16 @@ int64_t pmc_ctx_launch_count(pmc_ctx *ctx);
  * counterpart; results do not depend on them beyond the summation order of the Gram partials. */
 int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value);
 int pmc_ctx_get_option(pmc_ctx *ctx, const char *name, int *value);
+/* Per-launch kernel times.  With the option "kernel_timing" set to 1 the library brackets every launch of its
+ * tensor-core kernels (the Gram tile kernel: PMC_KERNEL_GRAM; the block lincomb kernel: PMC_KERNEL_LINCOMB) and of
+ * the CSR SpMM (PMC_KERNEL_SPMM) with CUDA events on the launching stream.  This call waits for the recorded
+ * launches, writes (kind, milliseconds) pairs in launch order, stores their number in *count and clears the log
+ * (at most PMC_TIMING_SLOTS = 1024 launches are kept).  No reference counterpart: measurement only (bench.py's
+ * `roofline` is the time of the kernel itself, not of the call around it). */
+#define PMC_KERNEL_GRAM 0
+#define PMC_KERNEL_LINCOMB 1
+#define PMC_KERNEL_SPMM 2
+int pmc_ctx_kernel_times(pmc_ctx *ctx, int32_t *kinds_out, double *ms_out, int32_t cap, int32_t *count);
 /* Pin caller-owned host memory (a shared-memory segment common to the ranks of one box) so that
  * reduction kernels can write their tiny partial results straight into it; *dev_ptr_out is the address
  * to pass as `out`.  The ranks then sum the partials on the host -- the replacement for the
@@ -197,6 +210,15 @@ int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32
                  const double *vals, const double *V, int64_t csV, int32_t kV, const double *U,
                  int64_t csU, int32_t kU, const double *ghost, double *out, int64_t ldo,
                  uint32_t flags);
+
+/* Fused CSR pairwise two-form  out[j] = sum_r V[r + j*csV] * (M U)[r, j],  j < k  (Operator.pairwise_apply2 =
+ * V.pairwise_inner(op.apply(U)), operators/interface.py:111-143 -- e.g. the product norms ||u_j||_M^2 that
+ * VectorArray.norm2(product) asks for): one pass over M, U and V, the n x k product M U is never written.
+ * `out`: k doubles, device or pinned host memory; block partials are summed in a fixed order (bitwise
+ * reproducible).  `ghost` as in pmc_csr_apply (for U). */
+int pmc_csr_pairwise(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
+                     const double *vals, const double *V, int64_t csV, const double *U, int64_t csU,
+                     const double *ghost, int32_t k, double *out, uint32_t flags);
 
 /* Roofline denominators measured on the spot: sustained FP64 tensor-core (DMMA) and DFMA
  * throughput in TFLOP/s over `ms` milliseconds of back-to-back issue on every SM.  use_dmma: 0 = DFMA, 1 = DMMA,

@@ -18,6 +18,7 @@ PMC_ERR_WORKSPACE = -3
 PMC_SYNC = 1
 PMC_SYMMETRIC = 2
 PMC_FORCE_SIMPLE = 4
+PMC_LOWER_ONLY = 8
 PMC_MAX_PEERS = 8
 PMC_IPC_HANDLE_BYTES = 64
 
@@ -42,6 +43,7 @@ _CTX_FUNCS = {
     'pmc_csr_apply': [_I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _U32],
     'pmc_gather_rows': [_P, _I64, _I32, _I64, _P, _I64, _P, _U32],
     'pmc_csr_gram': [_I64, _P, _P, _P, _P, _I64, _I32, _P, _I64, _I32, _P, _P, _I64, _U32],
+    'pmc_csr_pairwise': [_I64, _P, _P, _P, _P, _I64, _P, _I64, _P, _I32, _P, _U32],
     'pmc_measure_fp64_peak': [c_int, c_double, _P],
     'pmc_host_register': [_P, c_size_t, ctypes.POINTER(_P)],
     'pmc_host_unregister': [_P],
@@ -51,6 +53,7 @@ _CTX_FUNCS = {
     'pmc_peer_destroy': [],
     'pmc_ctx_set_option': [ctypes.c_char_p, c_int],
     'pmc_ctx_get_option': [ctypes.c_char_p, ctypes.POINTER(c_int)],
+    'pmc_ctx_kernel_times': [_P, _P, _I32, ctypes.POINTER(_I32)],
 }
 _OTHER_FUNCS = {
     'pmc_version': ([], c_int),
@@ -122,6 +125,7 @@ class DeviceContext:
         if rc != PMC_OK:
             raise PmcError(f'pmc_ctx_create failed: {self._err()}')
         self.handle = handle.value if isinstance(handle.value, int) else handle
+        self.stream_ptr = int(stream)                  # the stream the library launches on
         self._pin = on_cuda
         self._ws = None
         self.ensure_workspace(64 << 20)
@@ -252,6 +256,16 @@ class DeviceContext:
         out = c_int(0)
         self.call('pmc_ctx_get_option', name.encode(), ctypes.byref(out))
         return int(out.value)
+
+    KERNEL_KINDS = {0: 'gram', 1: 'lincomb', 2: 'spmm'}
+
+    def kernel_times(self):
+        """Per-launch times (ms) of the hot kernels recorded since the last call, as ``[(kind, ms), ...]`` in launch
+        order (``set_option('kernel_timing', 1)`` switches the recording on); waits for those launches."""
+        cap = 1024
+        kinds, ms, count = np.zeros(cap, dtype=np.int32), np.zeros(cap), _I32(0)
+        self.call('pmc_ctx_kernel_times', kinds.ctypes.data, ms.ctypes.data, cap, ctypes.byref(count))
+        return [(self.KERNEL_KINDS.get(int(kinds[i]), str(int(kinds[i]))), float(ms[i])) for i in range(count.value)]
 
     def measure_fp64_peak(self, use_dmma=True, ms=200.0):
         out = np.zeros(1)

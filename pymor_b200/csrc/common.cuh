@@ -11,6 +11,8 @@
 // ----------------------------------------------------------------------------------------------
 // context
 // ----------------------------------------------------------------------------------------------
+#define PMC_TIMING_SLOTS 1024
+
 struct pmc_ctx {
     int device;
     cudaStream_t stream;
@@ -36,7 +38,18 @@ struct pmc_ctx {
     int peer_rank, peer_size, peer_pending_size;
     uint64_t *peer_inbox_local;
     uint64_t *peer_inbox[PMC_MAX_PEERS];
+    // per-launch kernel times (option "kernel_timing"): event pairs around the launches of the hot kernels
+    int kernel_timing;
+    int t_count;
+    int t_kind[PMC_TIMING_SLOTS];
+    cudaEvent_t t_ev[PMC_TIMING_SLOTS][2];
 };
+
+// Bracket ONE kernel launch with events on the launching stream when the option "kernel_timing" is on
+// (bench.py's roofline: the time of the kernel itself, not of the call around it).  begin returns the slot
+// (-1: timing off or log full); end ignores -1.
+int pmc_timing_begin(pmc_ctx *ctx, int kind);
+void pmc_timing_end(pmc_ctx *ctx, int slot);
 
 void pmc_set_error(const char *fmt, ...);
 

@@ -117,9 +117,83 @@ __global__ void gather_rows_kernel(const double *__restrict__ A, int64_t csA, in
     out[t] = A[idx[r] + (int64_t)j * csA];
 }
 
+// Fused pairwise two-form  out[j] = sum_r V[r, j] * (M U)[r, j]  (Operator.pairwise_apply2 with a CSR operator, e.g.
+// the product norms ||u_j||_M^2 of every Gram-Schmidt step): the row of M U is formed in registers, multiplied with
+// the matching entry of V and reduced -- the n x k product M U is never written.  Every block owns a FIXED set of
+// row chunks and writes one partial per column; the second kernel sums the block partials in a fixed tree, so the
+// result is bitwise reproducible.
+constexpr int CP_MAXBLOCKS = 8 * 148;
+
+__global__ void __launch_bounds__(CSR_THREADS)
+csr_pairwise_kernel(int64_t nrows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                    const double *__restrict__ vals, const double *__restrict__ V, int64_t csV,
+                    const double *__restrict__ U, int64_t csU, const double *__restrict__ ghost, int k,
+                    double *__restrict__ partials /* [gridDim.y][gridDim.x][CJ] */) {
+    __shared__ double red[CSR_THREADS / 32][CJ];
+    const int j0 = blockIdx.y * CJ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double tot[CJ];
+#pragma unroll
+    for (int jj = 0; jj < CJ; ++jj) tot[jj] = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * CSR_THREADS + threadIdx.x; r < nrows;
+         r += (int64_t)gridDim.x * CSR_THREADS) {
+        const int64_t p0 = rowptr[r], p1 = rowptr[r + 1];
+        double acc[CJ];
+#pragma unroll
+        for (int jj = 0; jj < CJ; ++jj) acc[jj] = 0.0;
+        for (int64_t p = p0; p < p1; ++p) {
+            const double v = vals[p];
+            const int64_t col = colidx[p];
+            if (col < nrows) {
+                const double *x = U + col + (int64_t)j0 * csU;
+#pragma unroll
+                for (int jj = 0; jj < CJ; ++jj)
+                    if (j0 + jj < k) acc[jj] = fma(v, x[(int64_t)jj * csU], acc[jj]);
+            } else {
+                const double *gx = ghost + (col - nrows) * k + j0;
+#pragma unroll
+                for (int jj = 0; jj < CJ; ++jj)
+                    if (j0 + jj < k) acc[jj] = fma(v, gx[jj], acc[jj]);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < CJ; ++jj)
+            if (j0 + jj < k) tot[jj] = fma(ld_stream1(V + r + (int64_t)(j0 + jj) * csV), acc[jj], tot[jj]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < CJ; ++jj) {
+        const double s = warp_sum(tot[jj]);
+        if (lane == 0) red[warp][jj] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < CJ) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < CSR_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * CJ + threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+csr_pairwise_reduce_kernel(const double *__restrict__ partials, int nblocks, int k, double *__restrict__ out) {
+    __shared__ double red[256];
+    const int j = blockIdx.x;
+    const double *src = partials + ((size_t)(j / CJ) * nblocks) * CJ + (j % CJ);
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += src[(size_t)b * CJ];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[j] = red[0];
+}
+
 int launch_csr_apply(pmc_ctx *ctx, int64_t row0, int64_t nrows, const int64_t *rowptr,
                      const int32_t *colidx, const double *vals, const double *X, int64_t csX,
                      int64_t n_local, const double *ghost, double *Y, int64_t csY, int k) {
+    const int tslot = pmc_timing_begin(ctx, PMC_KERNEL_SPMM);
     if (ctx->csr_variant == 1) {
         dim3 grid((unsigned)ceil_div64(nrows, CT_ROWS), (k + CT_COLS - 1) / CT_COLS);
         csr_apply_tiled_kernel<<<grid, CT_ROWS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX,
@@ -129,6 +203,7 @@ int launch_csr_apply(pmc_ctx *ctx, int64_t row0, int64_t nrows, const int64_t *r
         csr_apply_kernel<<<grid, CSR_THREADS, 0, ctx->stream>>>(row0, nrows, rowptr, colidx, vals, X, csX,
                                                               n_local, ghost, Y, csY, k);
     }
+    pmc_timing_end(ctx, tslot);
     ctx->launches += 1;
     PMC_CHECK_CUDA(cudaGetLastError());
     return PMC_OK;
@@ -180,7 +255,10 @@ extern "C" int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, 
     double *T = static_cast<double *>(ctx->ws);
     void *gws = static_cast<char *>(ctx->ws) + panel_region;
     const size_t gws_cap = ctx->ws_bytes - panel_region;
-    const uint32_t gflags = flags & PMC_FORCE_SIMPLE;
+    // PMC_LOWER_ONLY: the caller knows the result is symmetric (V and U are the same panel and M is symmetric):
+    // only the tiles on/below the diagonal are contracted (half the flop), the rest is mirrored
+    PMC_REQUIRE(!(flags & PMC_LOWER_ONLY) || kV == kU, "PMC_LOWER_ONLY needs a square result");
+    const uint32_t gflags = flags & (PMC_FORCE_SIMPLE | PMC_LOWER_ONLY);
 
     int first = 1;
     for (int64_t r0 = 0; r0 < nrows; r0 += PR) {
@@ -193,6 +271,32 @@ extern "C" int pmc_csr_gram(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, 
         first = 0;
     }
     return pmc_after_launch(ctx, 0, flags);
+}
+
+extern "C" int pmc_csr_pairwise(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const int32_t *colidx,
+                                const double *vals, const double *V, int64_t csV, const double *U, int64_t csU,
+                                const double *ghost, int32_t k, double *out, uint32_t flags) {
+    PMC_REQUIRE(ctx && nrows >= 0 && k >= 0, "bad arguments");
+    if (k == 0) return pmc_after_launch(ctx, 0, flags);
+    PMC_REQUIRE(out != nullptr, "out is NULL");
+    if (nrows == 0) {
+        PMC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * k, ctx->stream));
+        return pmc_after_launch(ctx, 0, flags);
+    }
+    PMC_REQUIRE(rowptr && colidx && vals && V && U, "NULL pointer");
+    int64_t nb = ceil_div64(nrows, CSR_THREADS);
+    if (nb > CP_MAXBLOCKS) nb = CP_MAXBLOCKS;
+    const int groups = (k + CJ - 1) / CJ;
+    int rc = pmc_need_ws(ctx, (size_t)nb * groups * CJ * sizeof(double));
+    if (rc) return rc;
+    double *partials = static_cast<double *>(ctx->ws);
+    const int tslot = pmc_timing_begin(ctx, PMC_KERNEL_SPMM);
+    csr_pairwise_kernel<<<dim3((unsigned)nb, groups), CSR_THREADS, 0, ctx->stream>>>(
+        nrows, rowptr, colidx, vals, V, csV, U, csU, ghost, k, partials);
+    pmc_timing_end(ctx, tslot);
+    PMC_CHECK_CUDA(cudaGetLastError());
+    csr_pairwise_reduce_kernel<<<k, 256, 0, ctx->stream>>>(partials, (int)nb, k, out);
+    return pmc_after_launch(ctx, 2, flags);
 }
 
 extern "C" int pmc_gather_rows(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n,

@@ -75,6 +75,9 @@ extern "C" int pmc_ctx_destroy(pmc_ctx *ctx) {
     if (!ctx) return PMC_OK;
     cudaSetDevice(ctx->device);
     pmc_peer_destroy(ctx);
+    for (int i = 0; i < PMC_TIMING_SLOTS; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (ctx->t_ev[i][j]) cudaEventDestroy(ctx->t_ev[i][j]);
     cudaFree(ctx->sweep_box);
     cudaFree(ctx->tickets);
     cudaFree(ctx->partials);
@@ -106,12 +109,13 @@ static int *pmc_option_slot(pmc_ctx *ctx, const char *name) {
     if (!strcmp(name, "gram_waves")) return &ctx->gram_waves;
     if (!strcmp(name, "csr_variant")) return &ctx->csr_variant;
     if (!strcmp(name, "l2_keep")) return &ctx->l2_keep;
+    if (!strcmp(name, "kernel_timing")) return &ctx->kernel_timing;
     return nullptr;
 }
 
 extern "C" int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value) {
     int *slot = pmc_option_slot(ctx, name);
-    PMC_REQUIRE(slot != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep)");
+    PMC_REQUIRE(slot != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep, kernel_timing)");
     PMC_REQUIRE(slot != &ctx->gram_waves || value > 0, "gram_waves must be positive");
     *slot = value;
     return PMC_OK;
@@ -119,8 +123,39 @@ extern "C" int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value) {
 
 extern "C" int pmc_ctx_get_option(pmc_ctx *ctx, const char *name, int *value) {
     int *slot = pmc_option_slot(ctx, name);
-    PMC_REQUIRE(slot != nullptr && value != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep)");
+    PMC_REQUIRE(slot != nullptr && value != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep, kernel_timing)");
     *value = *slot;
+    return PMC_OK;
+}
+
+int pmc_timing_begin(pmc_ctx *ctx, int kind) {
+    if (!ctx->kernel_timing || ctx->t_count >= PMC_TIMING_SLOTS) return -1;
+    const int slot = ctx->t_count;
+    for (int j = 0; j < 2; ++j)
+        if (!ctx->t_ev[slot][j] && cudaEventCreate(&ctx->t_ev[slot][j]) != cudaSuccess) return -1;
+    if (cudaEventRecord(ctx->t_ev[slot][0], ctx->stream) != cudaSuccess) return -1;
+    ctx->t_kind[slot] = kind;
+    ctx->t_count = slot + 1;
+    return slot;
+}
+
+void pmc_timing_end(pmc_ctx *ctx, int slot) {
+    if (slot >= 0) cudaEventRecord(ctx->t_ev[slot][1], ctx->stream);
+}
+
+extern "C" int pmc_ctx_kernel_times(pmc_ctx *ctx, int32_t *kinds_out, double *ms_out, int32_t cap,
+                                    int32_t *count) {
+    PMC_REQUIRE(ctx && count && (cap == 0 || (kinds_out && ms_out)), "bad arguments");
+    const int n = ctx->t_count < cap ? ctx->t_count : cap;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        PMC_CHECK_CUDA(cudaEventSynchronize(ctx->t_ev[i][1]));
+        PMC_CHECK_CUDA(cudaEventElapsedTime(&ms, ctx->t_ev[i][0], ctx->t_ev[i][1]));
+        kinds_out[i] = ctx->t_kind[i];
+        ms_out[i] = (double)ms;
+    }
+    *count = n;
+    ctx->t_count = 0;
     return PMC_OK;
 }
 

@@ -46,7 +46,7 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int tile = item % p.ntiles, split = item / p.ntiles;
     int ti, tj;
     decode_tile(p, tile, ti, tj);
-    const bool diag = p.symmetric && ti == tj;
+    const bool diag = p.symmetric == 1 && ti == tj;   // (symmetric == 2: lower tiles of a general product, two operands)
     const int64_t r0 = (int64_t)split * p.rows_per_split;
     const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
     const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
@@ -264,7 +264,9 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
     if (kA == 0 || kB == 0) return pmc_after_launch(ctx, 0, flags);
     PMC_REQUIRE(out != nullptr && ldo >= kA, "bad output");
     const bool sym = (flags & PMC_SYMMETRIC) != 0;
+    const bool lower = !sym && (flags & PMC_LOWER_ONLY) != 0;
     if (sym) PMC_REQUIRE(A == B && csA == csB && kA == kB, "PMC_SYMMETRIC needs identical panels");
+    if (lower) PMC_REQUIRE(kA == kB, "PMC_LOWER_ONLY needs a square result");
     if (n == 0) {
         if (!accumulate)
             PMC_CHECK_CUDA(cudaMemset2DAsync(out, ldo * sizeof(double), 0, kA * sizeof(double), kB, ctx->stream));
@@ -284,10 +286,10 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
     p.kA = kA;
     p.kB = kB;
     p.opts = ctx->gram_opts;
-    p.symmetric = sym ? 1 : 0;
+    p.symmetric = sym ? 1 : lower ? 2 : 0;
     p.tiles_m = (kA + T - 1) / T;
     p.tiles_n = (kB + T - 1) / T;
-    p.ntiles = sym ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
+    p.ntiles = p.symmetric ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
 
     // split-n: aim at ~gram_waves full waves of CTAs (1 CTA/SM for the DMMA kernel), each item >= 64 steps
     const int64_t steps = ceil_div64(n, rows_q);
@@ -329,12 +331,13 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
         } else {
             tmW = tmA;
         }
-        if (p.opts & G2_OPT_ENABLE) {
+        if ((p.opts & G2_OPT_ENABLE) && p.symmetric != 2) {
             // second-generation tile kernel with its own reduction (gram2.cu)
             rc = pmc_gram2_launch(ctx, tmA, tmB, tmW, p, items, nsplit, w != nullptr, out, ldo, accumulate);
             if (rc) return rc;
             return pmc_after_launch(ctx, 2, flags);
         }
+        const int tslot = pmc_timing_begin(ctx, PMC_KERNEL_GRAM);
         if (w) {
             PMC_CHECK_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<true>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
@@ -344,6 +347,7 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
             gram_dmma_kernel<false><<<(unsigned)items, GRAM_THREADS, GRAM_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
         }
+        pmc_timing_end(ctx, tslot);
     } else {
         gram_simple_kernel<<<(unsigned)items, SM_THREADS, 0, ctx->stream>>>(A, csA, kA, B, csB, kB, w, p);
     }

@@ -40,9 +40,10 @@ constexpr size_t GRAM2_SMEM = 1024 /*align slack*/ + (size_t)STAGES * (2 * TILE_
 
 // One stage (16 rows = KS quarter-steps of 4) of a warp's block.  NM x NN sub-blocks of 8x8; TRI keeps
 // the sub-blocks with ni <= mi.  `fo` holds the fragment offsets of the warp's quarter-steps.
-template <int NM, int NN, bool TRI, int KS>
+// WREG: the diagonal weight of the fragment's row (w_s[wo[ks]]) multiplies the B fragments in registers.
+template <int NM, int NN, bool TRI, int KS, bool WREG>
 __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *a_s, const double *b_s,
-                                          const int (&fo)[4]) {
+                                          const int (&fo)[4], const double *w_s, const int (&wo)[4]) {
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         double a[NM], b[NN];
@@ -50,6 +51,12 @@ __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *
         for (int mi = 0; mi < NM; ++mi) a[mi] = a_s[mi * 8 * BK + fo[ks]];
 #pragma unroll
         for (int ni = 0; ni < NN; ++ni) b[ni] = b_s[ni * 8 * BK + fo[ks]];
+        if (WREG) {
+            const double wv = w_s[wo[ks]];
+            // fl(w * b) first, exactly as gram_dmma_kernel rounds
+#pragma unroll
+            for (int ni = 0; ni < NN; ++ni) b[ni] *= wv;
+        }
 #pragma unroll
         for (int mi = 0; mi < NM; ++mi)
 #pragma unroll
@@ -62,7 +69,9 @@ __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *
 // warp contracts half of the stage (2 quarter-steps), + 32 for a quarter; triangular (diagonal) blocks 48 + nm-1
 constexpr int SHAPE_IDLE = -1, SHAPE_TRI = 48;
 
-template <bool WEIGHTED>
+// WMODE: 0 no weight, 1 weight applied in shared memory once per stage (ready ring), 2 weight applied to the
+// fragments in registers
+template <int WMODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmW, const GramParams p) {
@@ -74,7 +83,9 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     double *sW = sB + STAGES * TILE_ELEMS;
     uint64_t *full = reinterpret_cast<uint64_t *>(sW + STAGES * BK);
     uint64_t *empty = full + STAGES;
-    uint64_t *ready = empty + STAGES;               // WEIGHTED: stage has been scaled by all warps
+    uint64_t *ready = empty + STAGES;               // WMODE 1: stage has been scaled by all warps
+    constexpr bool WEIGHTED = WMODE != 0;           // the weight tile is loaded
+    constexpr bool WSMEM = WMODE == 1, WREG = WMODE == 2;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -145,7 +156,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[s]);
     };
-    if (WEIGHTED) {
+    if (WSMEM) {
         const int pre = nk < LOOKAHEAD ? nk : LOOKAHEAD;
         for (int kt = 0; kt < pre; ++kt) scale_stage(kt);
     }
@@ -156,13 +167,16 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    int fo[4];
+    int fo[4], wo[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) fo[i] = g2_frag_offset((plan.ks0 + i) & 3, lane);
+    for (int i = 0; i < 4; ++i) {
+        fo[i] = g2_frag_offset((plan.ks0 + i) & 3, lane);
+        wo[i] = ((plan.ks0 + i) & 3) * 4 + (lane & 3);      // stage row of the fragment element: 4 * ks + t
+    }
     const int rho = g2_rho(lane >> 2);
     const int rowA = (plan.wm * 32 + rho) * BK;
     const int rowB = (plan.wn * 32 + rho) * BK;
-    const double *b_base = (diag && !WEIGHTED) ? sA : sB;
+    const double *b_base = (diag && !WSMEM) ? sA : sB;
 
     for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % STAGES;
@@ -172,26 +186,27 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty[sp], ((kt - 1) / STAGES) & 1);
             issue(kt - 1 + STAGES);
         }
-        mbar_wait(WEIGHTED ? &ready[s] : &full[s], (kt / STAGES) & 1);
+        mbar_wait(WSMEM ? &ready[s] : &full[s], (kt / STAGES) & 1);
         const double *a_s = sA + s * TILE_ELEMS + rowA;
         const double *b_s = b_base + s * TILE_ELEMS + rowB;
+        const double *w_s = sW + s * BK;
         switch (shape) {
 #define G2_RECT(NM, NN)                                                                                   \
-    case (NM - 1) * 4 + (NN - 1): stage_mma<NM, NN, false, 4>(acc, a_s, b_s, fo); break;                  \
-    case (NM - 1) * 4 + (NN - 1) + 16: stage_mma<NM, NN, false, 2>(acc, a_s, b_s, fo); break;             \
-    case (NM - 1) * 4 + (NN - 1) + 32: stage_mma<NM, NN, false, 1>(acc, a_s, b_s, fo); break;
+    case (NM - 1) * 4 + (NN - 1): stage_mma<NM, NN, false, 4, WREG>(acc, a_s, b_s, fo, w_s, wo); break;                  \
+    case (NM - 1) * 4 + (NN - 1) + 16: stage_mma<NM, NN, false, 2, WREG>(acc, a_s, b_s, fo, w_s, wo); break;             \
+    case (NM - 1) * 4 + (NN - 1) + 32: stage_mma<NM, NN, false, 1, WREG>(acc, a_s, b_s, fo, w_s, wo); break;
             G2_RECT(4, 4) G2_RECT(4, 3) G2_RECT(4, 2) G2_RECT(4, 1)
             G2_RECT(3, 4) G2_RECT(3, 3) G2_RECT(3, 2) G2_RECT(3, 1)
             G2_RECT(2, 4) G2_RECT(2, 3) G2_RECT(2, 2) G2_RECT(2, 1)
             G2_RECT(1, 4) G2_RECT(1, 3) G2_RECT(1, 2) G2_RECT(1, 1)
 #undef G2_RECT
-            case SHAPE_TRI + 3: stage_mma<4, 4, true, 4>(acc, a_s, b_s, fo); break;
-            case SHAPE_TRI + 2: stage_mma<3, 3, true, 4>(acc, a_s, b_s, fo); break;
-            case SHAPE_TRI + 1: stage_mma<2, 2, true, 4>(acc, a_s, b_s, fo); break;
-            case SHAPE_TRI + 0: stage_mma<1, 1, true, 4>(acc, a_s, b_s, fo); break;
+            case SHAPE_TRI + 3: stage_mma<4, 4, true, 4, WREG>(acc, a_s, b_s, fo, w_s, wo); break;
+            case SHAPE_TRI + 2: stage_mma<3, 3, true, 4, WREG>(acc, a_s, b_s, fo, w_s, wo); break;
+            case SHAPE_TRI + 1: stage_mma<2, 2, true, 4, WREG>(acc, a_s, b_s, fo, w_s, wo); break;
+            case SHAPE_TRI + 0: stage_mma<1, 1, true, 4, WREG>(acc, a_s, b_s, fo, w_s, wo); break;
             default: break;
         }
-        if (WEIGHTED && kt + LOOKAHEAD < nk) scale_stage(kt + LOOKAHEAD);
+        if (WSMEM && kt + LOOKAHEAD < nk) scale_stage(kt + LOOKAHEAD);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -264,15 +279,21 @@ __global__ void gram2_reduce_kernel(const double *__restrict__ partials, int nsp
 int pmc_gram2_launch(pmc_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmW,
                      const GramParams &p, int64_t items, int64_t nsplit, bool weighted, double *out,
                      int64_t ldo, int accumulate) {
-    if (weighted) {
-        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const int tslot = pmc_timing_begin(ctx, PMC_KERNEL_GRAM);
+    if (weighted && (p.opts & G2_OPT_W_SMEM)) {
+        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)GRAM2_SMEM));
-        gram2_dmma_kernel<true><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+        gram2_dmma_kernel<1><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+    } else if (weighted) {
+        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)GRAM2_SMEM));
+        gram2_dmma_kernel<2><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
     } else {
-        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)GRAM2_SMEM));
-        gram2_dmma_kernel<false><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+        gram2_dmma_kernel<0><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
     }
+    pmc_timing_end(ctx, tslot);
     PMC_CHECK_CUDA(cudaGetLastError());
     dim3 rgrid((BM * BN + 255) / 256, p.ntiles);
     gram2_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(p.partials, (int)nsplit, p, out, ldo, accumulate);

@@ -240,7 +240,9 @@ extern "C" int pmc_lincomb(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k
         PMC_REQUIRE(tiles < ((int64_t)1 << 31), "too many tiles");
         PMC_CHECK_CUDA(cudaFuncSetAttribute(lincomb_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)LINCOMB_SMEM));
+        const int tslot = pmc_timing_begin(ctx, PMC_KERNEL_LINCOMB);
         lincomb_dmma_kernel<<<(unsigned)tiles, LTHREADS, LINCOMB_SMEM, ctx->stream>>>(tmA, tmC, p);
+        pmc_timing_end(ctx, tslot);
     } else {
         dim3 grid((unsigned)ceil_div64(n, S_THREADS), (m + SJ - 1) / SJ);
         lincomb_simple_kernel<<<grid, S_THREADS, 0, ctx->stream>>>(A, csA, k, n, CT, ldc, m, R, csR);

@@ -21,6 +21,7 @@ import torch
 from pymor_b200.complexarray import CudaComplexVectorArrayImpl
 from pymor_b200.interface import Operator
 from pymor_b200.solvers import CgSolver, DiagonalSolver
+from pymor_b200._lib import PMC_LOWER_ONLY
 from pymor_b200.vectorarray import CudaVectorArray, CudaVectorArrayImpl, CudaVectorSpace
 
 
@@ -127,12 +128,18 @@ class _ShardedCsr:
     is the "MPI-aware operator" the reference leaves to external solvers
     (src/pymor/operators/mpi.py:22-26)."""
 
-    def __init__(self, csr, space):
+    def __init__(self, csr, space, rows_are_local=False):
         comm = space.comm
         lo, n = space.offset, space.local_dim
         hi = lo + n
-        local = sps.csr_matrix(csr[lo:hi])
+        if rows_are_local:          # this rank's row block only (n_local x dim, GLOBAL column numbers)
+            assert csr.shape == (n, space.dim)
+            local = sps.csr_matrix(csr)
+        else:                       # the global matrix: keep this rank's rows
+            local = sps.csr_matrix(csr[lo:hi])
         local.sort_indices()
+        # this rank's part of the matrix diagonal (Jacobi preconditioner of the device CG)
+        self.diag_local = np.asarray(local.diagonal(k=lo) if local.shape[1] > lo else np.zeros(0), dtype=np.float64)
         cols = local.indices.astype(np.int64)
         mine = (cols >= lo) & (cols < hi)
         ghosts = np.unique(cols[~mine])
@@ -164,6 +171,7 @@ class _ShardedCsr:
         self = cls.__new__(cls)
         self.rowptr, self.colidx, self.vals = rowptr.contiguous(), colidx.contiguous(), vals.contiguous()
         self.n_ghost, self.recv, self.send, self.needs_exchange = 0, {}, {}, False
+        self.diag_local = None
         return self
 
     def halo(self, space, ptr, cs, k):
@@ -181,8 +189,18 @@ class _ShardedCsr:
         for p, (first, count) in self.recv.items():
             recvs[p] = ghost[first:first + count]
         if space.device.type == 'cuda':
-            torch.cuda.current_stream(space.device).synchronize()   # packed buffers complete before NCCL reads
+            # The packing kernels ran on the library's stream; NCCL orders its transfers after the work queued on
+            # torch's CURRENT stream.  Normally those are the same stream (nothing to do); otherwise chain them with
+            # an event -- the host never waits.
+            cur = torch.cuda.current_stream(space.device)
+            lib_stream = space.ctx.stream_ptr
+            if lib_stream != cur.cuda_stream:
+                cur.wait_stream(torch.cuda.ExternalStream(lib_stream, device=space.device))
         space.comm.exchange(sends, recvs)
+        if space.device.type == 'cuda':
+            cur = torch.cuda.current_stream(space.device)
+            if space.ctx.stream_ptr != cur.cuda_stream:
+                torch.cuda.ExternalStream(space.ctx.stream_ptr, device=space.device).wait_stream(cur)
         return ghost
 
 
@@ -197,16 +215,24 @@ class CudaCsrOperator(Operator):
         block.  Couplings across shard boundaries are served by a halo exchange.
     space
         The :class:`CudaVectorSpace` (source and range).
+    symmetric
+        ``True`` / ``False``: the matrix is (not) symmetric; ``None``: checked on the host matrix on first use.
+        Symmetric operators compute ``apply2(V, V)`` on the lower tile triangle only (half the flop), use
+        ``apply`` for ``apply_adjoint`` and default to the device CG solver for ``apply_inverse``.
+
+    Use :meth:`from_local_rows` when the global matrix should not exist on every rank (each rank passes its own
+    row block), :meth:`from_device_csr` for CSR arrays that are already on the device.
     """
 
     linear = True
 
-    def __init__(self, matrix, space, solver=None, name=None):
+    def __init__(self, matrix, space, solver=None, name=None, symmetric=None):
         assert isinstance(space, CudaVectorSpace)
         self.matrix = matrix
         self.space = space
         self.name = name
         self.solver = solver
+        self.symmetric = symmetric
         self.source = self.range = space
         self._dev = None
         self._dev_T = None
@@ -216,10 +242,35 @@ class CudaCsrOperator(Operator):
             self._dev = _ShardedCsr(sps.csr_matrix(matrix), space)
 
     @classmethod
-    def from_device_csr(cls, rowptr, colidx, vals, space, name=None):
+    def from_local_rows(cls, local_rows, space, symmetric=False, solver=None, name=None):
+        """From THIS RANK's row block only: a SciPy sparse matrix of shape ``(space.local_dim, space.dim)`` holding
+        rows ``[space.offset, space.offset + space.local_dim)`` with GLOBAL column numbers.  No rank ever holds the
+        global matrix; the ghost map (which remote DOFs each rank needs, who sends what) is derived from the column
+        indices and agreed on once (one ``all_gather_object`` of the request lists).  ``apply_adjoint`` is available
+        for ``symmetric=True`` only (the transpose of a row-distributed matrix would need a redistribution)."""
+        op = cls(None, space, solver=solver, name=name, symmetric=bool(symmetric))
+        object.__setattr__(op, '_dev', _ShardedCsr(local_rows, space, rows_are_local=True))
+        return op
+
+    def is_symmetric(self):
+        """Whether the matrix is symmetric: the ``symmetric`` argument, else a host check cached on first use
+        (``False`` without a host matrix)."""
+        if self.symmetric is not None:
+            return bool(self.symmetric)
+        if '_symmetric' not in self.__dict__:
+            sym = False
+            if self.matrix is not None and self.matrix.shape[0]:
+                csr = sps.csr_matrix(self.matrix)
+                asym = abs(csr - csr.T)
+                sym = bool(asym.nnz == 0 or asym.max() <= 1e-14 * abs(csr).max())
+            object.__setattr__(self, '_symmetric', sym)
+        return self.__dict__['_symmetric']
+
+    @classmethod
+    def from_device_csr(cls, rowptr, colidx, vals, space, name=None, symmetric=False):
         """Adopt this rank's CSR block already on the device (int64 rowptr, int32 colidx with LOCAL
         column numbers, fp64 vals); no halo."""
-        op = cls(None, space, name=name)
+        op = cls(None, space, name=name, symmetric=symmetric)
         assert rowptr.dtype == torch.int64 and colidx.dtype == torch.int32 and vals.dtype == torch.float64
         object.__setattr__(op, '_dev', _ShardedCsr.from_device(rowptr, colidx, vals))
         return op
@@ -244,6 +295,8 @@ class CudaCsrOperator(Operator):
 
     def apply_adjoint(self, V, mu=None):
         assert V in self.range
+        if self.is_symmetric():
+            return self._apply_csr(self._dev, V)
         if self._dev_T is None:
             if self.matrix is None:
                 raise NotImplementedError('apply_adjoint needs the host matrix to build the transpose')
@@ -261,10 +314,14 @@ class CudaCsrOperator(Operator):
         sp, blk = self.space, self._dev
         ghost = blk.halo(sp, pu, csu, ku)
         out = torch.zeros(kv * ku, dtype=torch.float64, device=sp.device)   # accumulated on the device
+        # V^T (M V) with symmetric M is symmetric: contract the lower tile triangle only (SYRK flop count)
+        flags = sp.kernel_flags
+        if (pv, csv, kv) == (pu, csu, ku) and kv > 128 and self.is_symmetric():
+            flags |= PMC_LOWER_ONLY
         if sp.local_dim:
             sp.ctx.call('pmc_csr_gram', sp.local_dim, blk.rowptr.data_ptr(), blk.colidx.data_ptr(),
                         blk.vals.data_ptr(), pv, csv, kv, pu, csu, ku,
-                        ghost.data_ptr() if ghost is not None else 0, out.data_ptr(), kv, sp.kernel_flags)
+                        ghost.data_ptr() if ghost is not None else 0, out.data_ptr(), kv, flags)
         if sp.comm.size > 1:
             sp.comm.allreduce_sum_(out)
         del keep_v, keep_u
@@ -273,7 +330,22 @@ class CudaCsrOperator(Operator):
     def pairwise_apply2(self, V, U, mu=None):
         assert V in self.range and U in self.source
         assert len(V) == len(U)
-        return V.pairwise_inner(self.apply(U))
+        if _is_complex(V) or _is_complex(U):
+            return V.pairwise_inner(self.apply(U))
+        # fused: one pass over M, U and V; the n x k product M U (what operators/interface.py:111-143 materialises)
+        # is never written
+        pv, csv, kv, keep_v = V.impl._panel(V.ind)
+        pu, csu, ku, keep_u = U.impl._panel(U.ind)
+        if kv == 0:
+            return np.zeros(0)
+        sp, blk = self.space, self._dev
+        ghost = blk.halo(sp, pu, csu, ku)
+        out, flags = sp.reduction_target(kv)
+        sp.ctx.call('pmc_csr_pairwise', sp.local_dim, blk.rowptr.data_ptr(), blk.colidx.data_ptr(),
+                    blk.vals.data_ptr(), pv, csv, pu, csu, ghost.data_ptr() if ghost is not None else 0, kv,
+                    out.data_ptr(), flags)
+        del keep_v, keep_u
+        return sp.reduction_result(out, kv)
 
     def _assemble_lincomb(self, operators, coefficients, identity_shift=0., name=None):
         """pyMOR's hook for ``LincombOperator.assemble`` (reference counterpart: operators/numpy.py:243-287): a real
@@ -305,13 +377,7 @@ class CudaCsrOperator(Operator):
         matrices (mass / stiffness / energy products -- Riesz representatives ``product.apply_inverse(residual)``
         then stay on the device), ``None`` (pyMOR's default) otherwise.  Symmetry is checked on first use."""
         if '_default_solver' not in self.__dict__:
-            sol = None
-            if self.matrix is not None and self.matrix.shape[0]:
-                csr = sps.csr_matrix(self.matrix)
-                asym = abs(csr - csr.T)
-                if asym.nnz == 0 or asym.max() <= 1e-14 * abs(csr).max():
-                    sol = CgSolver()
-            object.__setattr__(self, '_default_solver', sol)
+            object.__setattr__(self, '_default_solver', CgSolver() if self.is_symmetric() else None)
         return self.__dict__['_default_solver']
 
     def apply_inverse(self, V, mu=None, initial_guess=None, return_info=False, solver=None):
@@ -324,14 +390,17 @@ class CudaCsrOperator(Operator):
                                              solver=solver)
 
     def jacobi_preconditioner(self):
-        """Inverse of the matrix diagonal as a :class:`CudaDiagonalOperator` (``None`` without the host matrix or
-        with a zero on the diagonal); cached."""
+        """Inverse of the matrix diagonal as a :class:`CudaDiagonalOperator` (``None`` with a zero on the diagonal or
+        for operators adopted from device CSR arrays); cached.  Collective on sharded spaces."""
         if '_jacobi' not in self.__dict__:
             jac = None
-            if self.matrix is not None:
-                d = np.asarray(sps.csr_matrix(self.matrix).diagonal(), dtype=np.float64)
-                if d.size and np.all(d != 0):
-                    jac = CudaDiagonalOperator(1.0 / d, self.space)
+            d = self._dev.diag_local if self._dev is not None else None
+            if d is not None and len(d) == self.space.local_dim:
+                ok = bool(np.all(d != 0))
+                if self.space.comm.size > 1:                       # all ranks must take the same branch
+                    ok = all(self.space.comm.allgather_object(ok))
+                if ok and self.space.dim:
+                    jac = CudaDiagonalOperator(torch.from_numpy(1.0 / d).to(self.space.device), self.space)
             object.__setattr__(self, '_jacobi', jac)
         return self.__dict__['_jacobi']
 

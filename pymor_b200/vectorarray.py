@@ -453,11 +453,11 @@ class CudaVectorArrayImpl(VectorArrayImpl):
             if c0:
                 ctx.call('pmc_gram', self._ptr(0), self.ld, c0, self._ptr(c0), self.ld, c1 - c0, self.n,
                          weight_ptr, base, k, 0)
-        self._arrival_src = None
         if flags & PMC_SYNC:
             ctx.sync()
         # the strictly lower blocks were never written: only the upper triangle of the scratch is used
         raw = sp.reduction_result(out, k * k).reshape((k, k), order='F')
+        self._arrival_src = None          # the host has synchronised: every block has left the staging buffer
         res = np.triu(raw)
         return res + np.triu(raw, 1).T
 
@@ -777,9 +777,26 @@ class CudaVectorSpace(VectorSpace):
             impl._buf[:count, :self._local_dim].copy_(torch.from_numpy(rows))
         return CudaVectorArray(self, impl)
 
+    def wait_uploads(self):
+        """Block the host until every host -> device upload started by :meth:`from_local_numpy` has left its
+        source buffer.  Call this before refilling a (pinned) staging buffer that was handed to
+        ``from_local_numpy`` -- the copies are asynchronous."""
+        ctx = self._ctx
+        if ctx.uploads:
+            ctx.wait_uploads()
+        if ctx._copy_stream is not None:
+            ctx._copy_stream.synchronize()
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream(self.device).synchronize()
+
     def from_local_numpy(self, shard, reserve=0):
         """Upload THIS RANK's rows: ``shard`` has shape ``(local_dim, len)``.  A Fortran-ordered
-        shard (one vector per contiguous column) in pinned memory is copied by a single DMA."""
+        shard (one vector per contiguous column) in pinned memory is copied by a single DMA.
+
+        The copy is ASYNCHRONOUS (device work is ordered after it; large pinned shards travel on a side stream
+        in column blocks and the first Gramian starts on the blocks as they land): the caller must not modify
+        ``shard`` until :meth:`wait_uploads` has returned or a result computed from the array has reached the
+        host."""
         shard = np.asarray(shard)
         if np.iscomplexobj(shard):
             re, im = self.from_local_numpy(shard.real, reserve), self.from_local_numpy(shard.imag, reserve)

@@ -70,7 +70,7 @@ class EmulatedLib:
         return self.launches
 
     def pmc_ctx_set_option(self, ctx, name, value):
-        if name not in (b'gram_opts', b'gram_waves', b'csr_variant', b'l2_keep'):
+        if name not in (b'gram_opts', b'gram_waves', b'csr_variant', b'l2_keep', b'kernel_timing'):
             self._err = b'unknown option'
             return PMC_ERR_INVALID
         self.options = getattr(self, 'options', {})
@@ -79,6 +79,10 @@ class EmulatedLib:
 
     def pmc_ctx_get_option(self, ctx, name, out):
         out._obj.value = getattr(self, 'options', {}).get(name, 0)
+        return PMC_OK
+
+    def pmc_ctx_kernel_times(self, ctx, kinds, ms, cap, count):
+        count._obj.value = 0                       # the emulation launches no kernels
         return PMC_OK
 
     def pmc_host_register(self, ctx, host_ptr, nbytes, out):
@@ -260,8 +264,16 @@ class EmulatedLib:
     def pmc_csr_gram(self, ctx, nrows, rowptr, colidx, vals, V, csV, kV, U, csU, kU, ghost, out, ldo, flags):
         self._note('pmc_csr_gram')
         g = _panel(V, csV, kV, nrows).T @ self._csr_times(nrows, rowptr, colidx, vals, U, csU, kU, ghost)
+        if flags & 8:                              # PMC_LOWER_ONLY: lower triangle computed, the rest mirrored
+            g = np.tril(g) + np.tril(g, -1).T
         o = _vec(out, ldo * kU).reshape((ldo, kU), order='F')
         o[:kV, :] = g
+        return PMC_OK
+
+    def pmc_csr_pairwise(self, ctx, nrows, rowptr, colidx, vals, V, csV, U, csU, ghost, k, out, flags):
+        self._note('pmc_csr_pairwise')
+        MU = self._csr_times(nrows, rowptr, colidx, vals, U, csU, k, ghost)
+        _vec(out, k)[:] = np.einsum('ij,ij->j', _panel(V, csV, k, nrows), MU) if nrows else 0.0
         return PMC_OK
 
     def pmc_measure_fp64_peak(self, ctx, use_dmma, ms, out):

@@ -1,5 +1,6 @@
-"""bench.py contract pieces that run without a GPU: the reference arm (oracle port on the host cores)
-prints one well-formed JSON line; the flop model matches SURVEY.md §8d."""
+"""bench.py contract pieces that run without a GPU: the reference arm (pyMOR's own NumPy backend through the same
+pod() call, on the host cores) prints one well-formed JSON line whose `config` equals the CUDA arm's; the flop model
+matches SURVEY.md §8d."""
 import json
 import subprocess
 import sys
@@ -16,8 +17,25 @@ def test_reference_arm_prints_contract_line():
                 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
         assert key in line, key
     assert line['impl'] == 'reference' and line['unit'] == 'TFLOP/s' and line['dtype'] == 'f64'
-    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'reference' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['vs_baseline'] is None
+    # same metric / config object as the CUDA arm would print for these arguments
+    sys.path.insert(0, str(ROOT))
+    import argparse
+
+    import bench
+    args = argparse.Namespace(n=100000, k=40, scaling='strong')
+    assert line['config'] == bench.workload_config(args, 1) and line['metric'] == bench.METRIC
+    assert line['scaling'] == 'strong'
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun (N > 1) rank 0 alone runs the reference arm; the other ranks exit 0 without work."""
+    import os
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    r = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+                        '--warmup', '0'], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ''
 
 
 def test_flop_model():

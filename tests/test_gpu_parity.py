@@ -81,10 +81,8 @@ def test_gram_parity(loaded_lib, rng, dim, ka, kb, weighted):
     sp.force_generic_kernels(False)
 
 
-# Second-generation Gram tile kernel (pymor_b200/csrc/gram2.cu, opt-in with gram_opts bit 16).  Written after the
-# round-1 GPU budget was spent: its index maps are CPU-checked (tests/test_gram2_model.py) but it has not
-# run on a B200 yet, so this test only runs on request (PMC_TEST_GRAM2=1, tools/gpu_session_r2_gram2.sh)
-# until it has been seen green once -- then drop the gate and, if the A/B favours it, make it the default.
+# Second-generation Gram tile kernel (pymor_b200/csrc/gram2.cu, gram_opts bit 16) against the oracle and the first
+# kernel, for every ablation bit incl. both ways of applying the diagonal weight (bit 256: in shared memory).
 def _block_error_map(G, G_ref, scale):
     """Max scaled error per 32x32 block (the unit a warp of the tile kernels owns) -- printed when a Gram parity
     assertion fails, so that one GPU session is enough to tell WHICH block / tile kind is wrong."""
@@ -98,8 +96,7 @@ def _block_error_map(G, G_ref, scale):
         return f'max scaled error per 32x32 block (rows = block row i, 4 blocks = one 128 tile):\n{m}'
 
 
-@pytest.mark.skipif(os.environ.get('PMC_TEST_GRAM2') != '1', reason='gram2 kernel awaits its first GPU session')
-@pytest.mark.parametrize('opts', [16, 16 | 32, 16 | 64, 16 | 128, 16 | 32 | 64 | 128])
+@pytest.mark.parametrize('opts', [16, 16 | 32, 16 | 64, 16 | 128, 16 | 32 | 64 | 128, 16 | 256, 16 | 64 | 256])
 def test_gram2_variant_parity(loaded_lib, rng, opts):
     from pymor_b200._lib import get_context
     from pymor_b200.operators import CudaDiagonalOperator
@@ -580,10 +577,8 @@ def test_next_row_empirical_interpolation_golden(loaded_lib):
     np.testing.assert_array_equal(basis.to_numpy(), g['deim_nopod_basis'])
 
 
-# Fused Gram-Schmidt sweep (pymor_b200/csrc/mgs.cu): written after the round-1 GPU budget was spent; host logic
-# and packet protocol are CPU-checked (tests/test_host_layer.py, tests/test_mgs_sweep_model.py).  Runs on request
-# (PMC_TEST_SWEEP=1, tools/gpu_session_r2_first.sh) until it has been seen green on a B200.
-@pytest.mark.skipif(os.environ.get('PMC_TEST_SWEEP') != '1', reason='mgs_sweep kernel awaits its first GPU session')
+# Fused Gram-Schmidt sweep (pymor_b200/csrc/mgs.cu); host logic and packet protocol are also CPU-checked
+# (tests/test_host_layer.py, tests/test_mgs_sweep_model.py).
 def test_mgs_sweep_parity(loaded_lib, rng):
     from pymor_b200 import algorithms as alg
     from pymor_b200.operators import CudaDiagonalOperator
@@ -652,7 +647,6 @@ def test_mgs_sweep_parity(loaded_lib, rng):
         assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, None if gprod is None else g['w'], tight=1e-11)
 
 
-@pytest.mark.skipif(os.environ.get('PMC_TEST_SWEEP') != '1', reason='late round-1 addition: runs on request')
 def test_device_cg_solver(loaded_lib, rng):
     """apply_inverse of an SPD CSR operator by block conjugate gradients on the device (Riesz representatives of
     the reductors' error estimators): 2-D 5-point Laplacian + mass shift, 40k DOFs, 6 right-hand sides."""

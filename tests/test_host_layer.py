@@ -198,8 +198,15 @@ def test_standalone_gram_schmidt_golden(emu, name):
     VA = sp.from_numpy(g['A'])
     Q, R = alg.gram_schmidt(VA, product=prod, return_R=True)
     np.testing.assert_array_equal(VA.to_numpy(), g['A'])        # copy=True leaves the input alone
-    np.testing.assert_allclose(Q.to_numpy(), g[f'Q_{name}'], atol=1e-11)
-    np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
+    if name == 'csr':
+        # the fused pairwise two-form (pmc_csr_pairwise) sums v_r (M u)_r in one pass: rounding differs from the
+        # reference's apply-then-dot, which the near-dependent column of this input amplifies by 1e9
+        from conftest import assert_gram_schmidt_golden
+        assert_gram_schmidt_golden(Q.to_numpy(), R, g, name, csr_from(g, 'M'))
+        assert 'pmc_csr_pairwise' in emu.calls
+    else:
+        np.testing.assert_allclose(Q.to_numpy(), g[f'Q_{name}'], atol=1e-11)
+        np.testing.assert_allclose(R, g[f'R_{name}'], atol=1e-11)
     Q0 = alg.gram_schmidt(sp.from_numpy(g['A'][:, :4]))
     Q0.append(sp.from_numpy(g['A'][:, 10:]))
     if name == 'euclid':
