@@ -345,6 +345,57 @@ def test_csr_twoform_multi_panel(loaded_lib, rng):
     np.testing.assert_allclose(op.apply(sp.from_numpy(U[:, :7])).to_numpy(), MU[:, :7], rtol=1e-13, atol=1e-13)
 
 
+def test_csr_pairwise_and_symmetric_twoform(loaded_lib, rng):
+    """The fused pairwise two-form (pmc_csr_pairwise: no n x k temporary, fixed summation tree) and the
+    lower-triangle-only two-form of a symmetric operator (PMC_LOWER_ONLY) against the oracle; the per-rank
+    constructor `from_local_rows`."""
+    from pymor_b200.operators import CudaCsrOperator
+    for dim, k in ((1, 3), (777, 5), (60000, 300), (400003, 130)):
+        M = (sps.diags([-np.ones(dim - 1), 2.5 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1])).tocsr()
+        if dim > 1000:
+            R = sps.random(dim, dim, density=2e-5, random_state=3)
+            M = (M + R + R.T).tocsr()                                  # symmetric, irregular rows
+        sp = space_of(dim)
+        V, U = rng.standard_normal((dim, k)), rng.standard_normal((dim, k))
+        VV, UU = sp.from_numpy(V), sp.from_numpy(U)
+        op = CudaCsrOperator(M, sp)
+        MU = M @ U
+        p = op.pairwise_apply2(VV, UU)
+        ref = np.einsum('ij,ij->j', V, MU)
+        scale = np.linalg.norm(V, axis=0) * np.linalg.norm(MU, axis=0)
+        assert np.max(np.abs(p - ref) / scale) < GRAM_TOL
+        np.testing.assert_array_equal(p, op.pairwise_apply2(VV, UU))      # fixed summation order
+        np.testing.assert_allclose(UU.norm(op), np.sqrt(np.einsum('ij,ij->j', U, MU)), rtol=1e-12)
+        assert op.is_symmetric()
+        G = op.apply2(UU, UU)                                             # lower tiles only for k > 128
+        assert O.gram_rel_error(G, U.T @ MU, U, MU) < GRAM_TOL
+        np.testing.assert_array_equal(G, G.T)
+        loc = CudaCsrOperator.from_local_rows(M, sp, symmetric=True)
+        np.testing.assert_array_equal(loc.apply2(UU, UU), G)
+        np.testing.assert_array_equal(loc.apply(UU[:3]).to_numpy(), op.apply(UU[:3]).to_numpy())
+        G2 = op.apply2(VV, UU)                                            # general pair: full product
+        assert O.gram_rel_error(G2, V.T @ MU, V, MU) < GRAM_TOL
+
+
+def test_kernel_timing_log(loaded_lib, rng):
+    """pmc_ctx_kernel_times: one (kind, ms) pair per launch of the tensor-core / SpMM kernels while the option is on."""
+    from pymor_b200._lib import get_context
+    ctx = get_context('cuda')
+    sp = space_of(50000)
+    A = sp.from_numpy(rng.standard_normal((50000, 64)))
+    ctx.kernel_times()
+    A.gramian()
+    assert ctx.kernel_times() == []                                       # off by default
+    ctx.set_option('kernel_timing', 1)
+    try:
+        A.gramian(); A.lincomb(np.eye(64)); A.gramian()
+        log = ctx.kernel_times()
+    finally:
+        ctx.set_option('kernel_timing', 0)
+    assert [kind for kind, _ in log] == ['gram', 'lincomb', 'gram'] and all(0 < ms < 100 for _, ms in log)
+    assert ctx.kernel_times() == []
+
+
 def test_full_size_properties(loaded_lib):
     """Size-independent properties at a BASELINE-scale shape (config 2: 2M DOF x 500 snapshots):
     linearity of the Gramian, ||A c|| consistency between lincomb and Gramian, POD orthonormality and

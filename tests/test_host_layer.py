@@ -186,6 +186,44 @@ def test_product_operators_fused_paths(emu, rng, kind):
         assert emu.calls.count('pmc_diag_apply') == 2
     else:
         assert emu.calls.count('pmc_csr_gram') == 3
+        assert emu.calls.count('pmc_csr_pairwise') == 2 and emu.calls.count('pmc_csr_apply') == 2   # no M U temporary
+
+
+def test_csr_operator_symmetric_lower_only_and_local_rows(emu, rng):
+    """V^T (M V) with symmetric M is contracted on the lower tile triangle only (PMC_LOWER_ONLY) and mirrored;
+    a non-symmetric M never is.  `from_local_rows` (this rank's row block, global column numbers) equals the
+    operator built from the global matrix; symmetric operators serve apply_adjoint with apply."""
+    from pymor_b200.operators import CudaCsrOperator
+    dim, k = 300, 140                               # k > 128: more than one tile row
+    h = 1.0 / (dim + 1)
+    P = sps.diags([np.full(dim - 1, h / 6), np.full(dim, 4 * h / 6), np.full(dim - 1, h / 6)], [-1, 0, 1]).tocsr()
+    N = (P + sps.random(dim, dim, density=0.02, random_state=5)).tocsr()
+    sp = space_of(dim)
+    A = rng.standard_normal((dim, k))
+    VA = sp.from_numpy(A)
+    seen = []
+    orig = emu.pmc_csr_gram
+    emu.pmc_csr_gram = lambda *a: (seen.append(a[-1]), orig(*a))[1]
+    try:
+        for M, want in ((P, 8), (N, 0)):
+            op = CudaCsrOperator(M, sp)
+            G = op.apply2(VA, VA)
+            np.testing.assert_allclose(G, A.T @ (M @ A), atol=1e-13)
+            assert seen[-1] & 8 == want
+            op.apply2(VA[:100], VA)                 # different panels: never lower-only
+            assert seen[-1] & 8 == 0
+    finally:
+        emu.pmc_csr_gram = orig
+    loc = CudaCsrOperator.from_local_rows(P[sp.offset:sp.offset + sp.local_dim], sp, symmetric=True)
+    np.testing.assert_allclose(loc.apply(VA[:5]).to_numpy(), P @ A[:, :5], atol=1e-14)
+    np.testing.assert_allclose(loc.apply_adjoint(VA[:5]).to_numpy(), P.T @ A[:, :5], atol=1e-14)
+    np.testing.assert_allclose(loc.apply2(VA, VA), A.T @ (P @ A), atol=1e-13)
+    np.testing.assert_allclose(VA[:9].norm(loc), O.norm(A[:, :9], P), atol=1e-13)
+    X = loc.apply_inverse(loc.apply(VA[:3]))        # symmetric => device CG with the Jacobi preconditioner
+    np.testing.assert_allclose(X.to_numpy(), A[:, :3], atol=1e-7)
+    nonsym = CudaCsrOperator.from_local_rows(N[sp.offset:sp.offset + sp.local_dim], sp)
+    with pytest.raises(NotImplementedError):
+        nonsym.apply_adjoint(VA[:2])
 
 
 @pytest.mark.parametrize('name', ['euclid', 'diag', 'csr'])
