@@ -45,6 +45,9 @@ def parse_args(argv):
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer legs (profiling runs)')
     ap.add_argument('--no-weak', action='store_true', help='N > 1: skip the extra weak-scaling measurement')
     ap.add_argument('--no-parity', action='store_true', help='skip the parity block')
+    ap.add_argument('--c5', default='auto', choices=['auto', 'on', 'off'],
+                    help="secondary block: BASELINE config 5, project() of a 5-point CSR operator onto 2000 basis vectors, "
+                         "6.25M DOF per GPU (50M at 8 GPUs); auto = at 8 GPUs")
     ap.add_argument('--accelerate', action='store_true',
                     help='also time pod() with pymor_b200.accelerate_pymor() active (extra key, never the headline)')
     return ap.parse_args(argv)
@@ -401,11 +404,15 @@ def run_cuda(args):
     try:
         if args.no_e2e:
             raise RuntimeError('skipped (--no-e2e)')
-        e2e = e2e_legs(args, space, A, prod, world, n_global, timed_loop, pod_step, device)
+        host, k_host = pinned_copy_of(A, world)
+        del A                                             # the e2e legs re-create the array from the host copy
+        torch.cuda.empty_cache()
+        e2e = e2e_legs(args, space, host, k_host, prod, world, n_global, timed_loop, pod_step, device)
     except Exception as exc:                              # e.g. not enough host RAM to pin the shard
         e2e = {'value': None, 'unit': 'TFLOP/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
                'error': f'{type(exc).__name__}: {exc}'}
-    del A, prod, w, space
+    A = None
+    del prod, w, space
     torch.cuda.empty_cache()
 
     # ---- N > 1: the weak-scaling figure next to the strong one ---------------------------------------------
@@ -439,6 +446,7 @@ def run_cuda(args):
                         'sample': f'the unmodified reference (pyMOR {_pymor_version()} NumPy backend) through the same pod() '
                                   f'call on a {n_s} x {k} row sample, 1 run'}
 
+    line = None
     if rank == 0:
         cfg = workload_config(args, world)
         cfg.update({'n_per_gpu': n_local, 'modes_kept': int(m)})
@@ -452,9 +460,34 @@ def run_cuda(args):
                           'device_tflops_excl_host_eigh': flop_global / ((t_step - eigh_mean) * 1e-3) * 1e-12,
                           'host_blas_threads_per_rank': host_threads()},
             'roofline': roofline, 'parity': parity, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'weak': weak,
-            'accelerated': accelerated, 'gpu_launches': int(launches), 'clocks': clocks,
+            'secondary': None, 'accelerated': accelerated, 'gpu_launches': int(launches), 'clocks': clocks,
         }
-        print(json.dumps(line))
+
+    # ---- secondary: BASELINE config 5 (RB projection V^T A V, 50M DOF x 2000 basis at 8 GPUs) ---------------
+    # Runs last and under a watchdog: whatever happens here, the contract line above is printed exactly once.
+    if args.c5 == 'on' or (args.c5 == 'auto' and world == 8):
+        def give_up():
+            if rank == 0:
+                line['secondary'] = {'projection_c5': {'error': 'timed out after 300 s'}}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        watchdog = threading.Timer(300.0, give_up)
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            sys.path.insert(0, str(ROOT / 'tools'))
+            from bench_project import run_projection
+            nx, ny = 5000, 1250 * world                    # 6.25M DOF per GPU; the shard boundary is one grid line
+            pspace = CudaVectorSpace(nx * ny, device=device, comm=comm)
+            barrier()
+            result = run_projection(pspace, nx, ny, 2000, reps=2, comm=comm)
+        except Exception as exc:
+            result = {'error': f'{type(exc).__name__}: {exc}'}
+        watchdog.cancel()
+        if rank == 0:
+            line['secondary'] = {'projection_c5': result}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -504,14 +537,15 @@ def parity_block(args, space, A, w, prod, comm, device, pod_step):
                          method='method_of_snapshots')
         Ur = Uref.to_numpy()
         mm = min(len(s), len(sref))
-        # principal angle between the two POD subspaces in the W inner product
-        sv = np.linalg.svd((Ur[:, :mm] * wh[:, None]).T @ Ug[:, :mm], compute_uv=False)
-        cosmin = float(min(1.0, sv.min()))
+        # largest principal angle between the two POD subspaces in the W inner product, from its SINE:
+        # || (I - Ur Ur^T W) Ug ||_2 (small angles are invisible in the cosines)
+        resid = Ug[:, :mm] - Ur[:, :mm] @ ((Ur[:, :mm] * wh[:, None]).T @ Ug[:, :mm])
+        sine = float(np.sqrt(np.linalg.norm((resid * wh[:, None]).T @ resid, 2)))
         out['sample'] = {
             'rows': int(host.shape[0]), 'k': k, 'reference': f'pyMOR {_pymor_version()} NumPy backend, same pod() call, same bits',
             'modes_kept': [int(len(s)), int(len(sref))],
             'singular_values_max_rel_err': float(np.max(np.abs(s[:mm] - sref[:mm]) / sref[:mm])),
-            'subspace_angle_rad': float(np.sqrt(max(0.0, 2.0 * (1.0 - cosmin)))),
+            'subspace_angle_rad': float(np.arcsin(min(1.0, sine))),
             'orth_err_device': float(np.max(np.abs((Ug * wh[:, None]).T @ Ug - np.eye(Ug.shape[1])))),
             'orth_err_reference': float(np.max(np.abs((Ur * wh[:, None]).T @ Ur - np.eye(Ur.shape[1])))),
             'tolerances': {'singular_values_rel': 1e-10, 'subspace_angle': 1e-8}}
@@ -526,23 +560,20 @@ def parity_block(args, space, A, w, prod, comm, device, pod_step):
     out['full_size'] = {
         'orth_err_max_abs(U^T W U - I)': float(np.max(np.abs(G - np.eye(len(U))))),
         'trace_identity_rel_err(sum s^2 vs sum ||a_j||_W^2)': float(abs(np.sum(s ** 2) - trace_norms) / trace_norms),
+        'sum_s2': float(np.sum(s ** 2)), 'sum_norm2': trace_norms,
         'gram_bitwise_symmetric': bool(np.array_equal(G, G.T)),
         'singular_values_sorted': bool(np.all(np.diff(s) <= 0)), 'modes_kept': int(len(U))}
     del U
     return out
 
 
-def e2e_legs(args, space, A, prod, world, n_global, timed_loop, pod_step, device):
-    """The same call measured end to end through the public API with HOST buffers: every step copies this rank's
-    snapshot shard from pinned host memory to the device (`space.from_local_numpy`), runs pod(), and reads the result
-    back.  Leg 1 (the `e2e` value): all modes kept, singular values come back, the modes stay on the device (where
-    the next pyMOR step -- projection -- uses them).  Leg 2 (`modes100`): pod(modes=100), the 100 modes are copied
-    back to pinned host memory as well."""
+def pinned_copy_of(A, world):
+    """This rank's snapshot shard in pinned host memory -- the starting point of the e2e legs.  One rank's shard is
+    n_local x k doubles; if the host cannot pin all shards at once (N ranks share one host), the buffer holds as
+    many snapshot columns as a 45 % share of the free host memory allows and is re-used for the later chunks (every
+    byte is still copied inside the timed region)."""
     import torch
-    k, n_local = args.k, space.local_dim
-    # The snapshots start in pinned host memory.  One rank's shard is n_local x k doubles; if the host cannot pin
-    # all shards at once (N ranks share one host), the buffer holds as many snapshot columns as a 45 % share of the
-    # free host memory allows and is re-used for the later chunks (every byte is still copied inside the timed region).
+    k, n_local = len(A), A.space.local_dim
     avail = psutil_available()
     k_host = int(min(k, max(1, (0.45 * avail / world) // (n_local * 8))))
     host = None
@@ -554,6 +585,17 @@ def e2e_legs(args, space, A, prod, world, n_global, timed_loop, pod_step, device
                 raise
             k_host = max(8, k_host // 2)
     host.copy_(A.to_torch()[:k_host])
+    return host, k_host
+
+
+def e2e_legs(args, space, host, k_host, prod, world, n_global, timed_loop, pod_step, device):
+    """The same call measured end to end through the public API with HOST buffers: every step copies this rank's
+    snapshot shard from pinned host memory to the device (`space.from_local_numpy`), runs pod(), and reads the result
+    back.  Leg 1 (the `e2e` value): all modes kept, singular values come back, the modes stay on the device (where
+    the next pyMOR step -- projection -- uses them).  Leg 2 (`modes100`): pod(modes=100), the 100 modes are copied
+    back to pinned host memory as well."""
+    import torch
+    k, n_local = args.k, space.local_dim
     host_np = host.numpy().T                          # (n_local, k_host) Fortran-ordered view
     h2d = k * n_local * 8
     last = {}

@@ -47,6 +47,7 @@ typedef enum {
 #define PMC_SYNC 1u        /* synchronise the stream before returning (results visible on host) */
 #define PMC_SYMMETRIC 2u   /* pmc_gram: B is the same panel as A -> SYRK (lower tiles + mirror)  */
 #define PMC_FORCE_SIMPLE 4u /* use the generic DFMA kernel even where the TMA/DMMA path applies (tests) */
+#define PMC_LOCAL_ONLY 16u /* pmc_mgs_sweep: this array lives on this GPU alone -- no sums with the connected peer GPUs */
 #define PMC_LOWER_ONLY 8u  /* pmc_gram / pmc_csr_gram: the caller knows the (square) result is symmetric although the two
                               operands differ (V^T (M V) with symmetric M): contract only the tiles on/below the diagonal
                               and mirror -- half the flop */
@@ -170,6 +171,13 @@ int pmc_copy(pmc_ctx *ctx, double *D, int64_t csD, const double *S, int64_t csS,
  * ld; idx is a HOST array.  Replaces fancy indexing `self._array[:, ind]` (numpy.py:21, :59). */
 int pmc_gather_cols(pmc_ctx *ctx, double *D, int64_t csD, const double *base, int64_t ld,
                     const int64_t *idx, int32_t k, int64_t n, uint32_t flags);
+
+/* In-place compaction: columns [first, first + count) of the panel move `shift` <= first columns down
+ * (A[:, c - shift] = A[:, c] for increasing c; ranges may overlap).  What `del array[...]` needs after the removed
+ * vectors are gone (NumpyVectorArrayImpl.delete re-allocates instead, vectorarrays/numpy.py:47-57): one launch per
+ * run of kept vectors. */
+int pmc_shift_cols(pmc_ctx *ctx, double *A, int64_t cs, int64_t first, int64_t count, int64_t shift,
+                   int64_t n, uint32_t flags);
 
 /* dofs: out[i + c*ndofs] = A[dof[i] + c*csA]; dof is a HOST array of local row indices.
  * Replaces NumpyVectorArrayImpl.dofs (numpy.py:196-201). */

@@ -19,6 +19,7 @@ PMC_SYNC = 1
 PMC_SYMMETRIC = 2
 PMC_FORCE_SIMPLE = 4
 PMC_LOWER_ONLY = 8
+PMC_LOCAL_ONLY = 16
 PMC_MAX_PEERS = 8
 PMC_IPC_HANDLE_BYTES = 64
 
@@ -37,6 +38,7 @@ _CTX_FUNCS = {
     'pmc_axpy_dot': [_P, _P, _P, _P, _I64, _P, _P, _U32],
     'pmc_copy': [_P, _I64, _P, _I64, _I32, _I64, _U32],
     'pmc_gather_cols': [_P, _I64, _P, _I64, _P, _I32, _I64, _U32],
+    'pmc_shift_cols': [_P, _I64, _I64, _I64, _I64, _I64, _U32],
     'pmc_dofs': [_P, _I64, _I32, _I64, _P, _I32, _P, _U32],
     'pmc_amax': [_P, _I64, _I32, _I64, _P, _P, _U32],
     'pmc_diag_apply': [_P, _P, _I64, _P, _I64, _I32, _I64, _U32],
@@ -138,6 +140,8 @@ class DeviceContext:
         self.fuse_axpy = os.environ.get('PMC_NO_FUSE_AXPY', '0') != '1'
         self.scalar = np.zeros(1)                      # staging for scalar coefficients (read at launch)
         self.scalar_ptr = self.scalar.ctypes.data
+        self._coeff_stage = None
+        self._coeff_event = None
         self._host_f64 = torch.empty(1 << 16, dtype=torch.float64, pin_memory=self._pin)
         self._host_i64 = torch.empty(1 << 12, dtype=torch.int64, pin_memory=self._pin)
 
@@ -193,6 +197,34 @@ class DeviceContext:
             self.scalar[0] = alpha
             self.call('pmc_axpy', timpl._ptr(tcol), timpl.ld, ximpl._ptr(xcol), ximpl.ld, 1, timpl.n,
                       self.scalar_ptr, 1, 0)
+
+    def upload_coefficients(self, coefficients, k, m, ldc):
+        """Host coefficient matrix ``(k, m)`` -> device tensor ``(m, ldc)`` (= Fortran-ordered ``(ldc, m)``) through a
+        pinned staging buffer and one asynchronous DMA on the compute stream.  The staging buffer is re-used: the
+        event of the previous upload is waited for before it is overwritten."""
+        if not self._pin:                                   # injected test library: plain host tensors
+            host = np.zeros((ldc, m), dtype=np.float64, order='F')
+            host[:k] = coefficients
+            return torch.from_numpy(host.T).to(self.device)
+        count = ldc * m
+        stage = self._coeff_stage
+        if stage is None or stage.numel() < count:
+            if self._coeff_event is not None:
+                self._coeff_event.synchronize()
+            stage = self._coeff_stage = torch.empty(max(int(count), 1 << 16), dtype=torch.float64, pin_memory=True)
+        elif self._coeff_event is not None:
+            self._coeff_event.synchronize()
+        view = stage[:count].numpy().reshape((ldc, m), order='F')
+        view[:k] = coefficients
+        if ldc > k:
+            view[k:] = 0.0
+        ct = torch.empty((m, ldc), dtype=torch.float64, device=self.device)
+        ct.copy_(stage[:count].view(m, ldc), non_blocking=True)
+        ev = self._coeff_event
+        if ev is None:
+            ev = self._coeff_event = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return ct
 
     def host_f64(self, count):
         """Pinned (device-writable) host buffer of at least ``count`` doubles."""

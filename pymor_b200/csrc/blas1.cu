@@ -333,6 +333,25 @@ gather_cols_kernel(double *__restrict__ D, int64_t csD, const double *__restrict
     }
 }
 
+// In-place compaction after `del A[...]`: columns [first, first + count) move `shift` columns down.  Source and
+// destination ranges overlap when count > shift, so every thread owns a set of ROWS and walks the columns in
+// increasing order: a column is read (by the same thread) before the move of a later column overwrites it, and
+// rows never interact.  One launch per run of kept columns whatever its length.
+__global__ void __launch_bounds__(TPB)
+shift_cols_kernel(double *__restrict__ A, int64_t cs, int64_t first, int64_t count, int64_t shift, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * TPB * 2;
+    for (int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 2; i < n; i += stride) {
+        if (i + 1 < n) {
+            for (int64_t c = first; c < first + count; ++c) {
+                const double2 v = *reinterpret_cast<const double2 *>(A + c * cs + i);
+                *reinterpret_cast<double2 *>(A + (c - shift) * cs + i) = v;
+            }
+        } else {
+            for (int64_t c = first; c < first + count; ++c) A[(c - shift) * cs + i] = A[c * cs + i];
+        }
+    }
+}
+
 __global__ void dofs_kernel(const double *__restrict__ A, int64_t csA, int k, IndexPack dof, int nd,
                             int ndofs_total, int dof0, double *__restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -494,6 +513,19 @@ extern "C" int pmc_gather_cols(pmc_ctx *ctx, double *D, int64_t csD, const doubl
         ++launches;
     }
     return pmc_after_launch(ctx, launches, flags);
+}
+
+extern "C" int pmc_shift_cols(pmc_ctx *ctx, double *A, int64_t cs, int64_t first, int64_t count, int64_t shift,
+                              int64_t n, uint32_t flags) {
+    PMC_REQUIRE(ctx && first >= 0 && count >= 0 && shift >= 0 && shift <= first && n >= 0, "bad arguments");
+    if (count == 0 || shift == 0 || n == 0) return pmc_after_launch(ctx, 0, flags);
+    PMC_REQUIRE(A && cs >= n && (cs % 2) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0,
+                "pmc_shift_cols needs a 16-byte aligned panel with an even column stride >= n");
+    int64_t blocks = ceil_div64(n, 2 * TPB);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    shift_cols_kernel<<<(unsigned)blocks, TPB, 0, ctx->stream>>>(A, cs, first, count, shift, n);
+    return pmc_after_launch(ctx, 1, flags);
 }
 
 extern "C" int pmc_dofs(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, int64_t n,

@@ -62,7 +62,7 @@ extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
     const char *nk = getenv("PMC_NO_L2_KEEP");
     c->l2_keep = (nk && nk[0] == '1') ? 0 : 1;
     const char *go = getenv("PMC_GRAM_OPTS");
-    c->gram_opts = go ? atoi(go) : 0;
+    c->gram_opts = go ? atoi(go) : 16;   // 16 = G2_OPT_ENABLE: gram2_dmma_kernel (A/B on B200: profiles/r02_summary.md); 0 = gram_dmma_kernel
     const char *cv = getenv("PMC_CSR_VARIANT");
     c->csr_variant = cv ? atoi(cv) : 0;
     const char *gw = getenv("PMC_GRAM_WAVES");

@@ -256,8 +256,13 @@ extern "C" int pmc_mgs_sweep(pmc_ctx *ctx, const double *Q, int64_t csQ, const d
     p.abort_flag = ctx->sweep_abort;
     p.seq_base = ctx->sweep_seq;
     ctx->sweep_seq += (uint32_t)nq + 1u;           // wraps after 2^32 steps; stale flags are long overwritten
-    p.rank = ctx->peer_size > 1 ? ctx->peer_rank : 0;
-    p.size = ctx->peer_size > 1 ? ctx->peer_size : 1;
+    // which GPUs take part is the CALLER's statement (PMC_LOCAL_ONLY: the array lives on this GPU alone, also when
+    // the context has peers connected for some other, sharded array)
+    const bool shared = ctx->peer_size > 1 && !(flags & PMC_LOCAL_ONLY);
+    p.rank = shared ? ctx->peer_rank : 0;
+    p.size = shared ? ctx->peer_size : 1;
+    // a wait that timed out in an earlier sweep must not abort this one (the flag is reported per call)
+    PMC_CHECK_CUDA(cudaMemsetAsync(ctx->sweep_abort, 0, sizeof(unsigned int), ctx->stream));
     p.inbox = ctx->peer_inbox_local;
     for (int r = 0; r < PMC_MAX_PEERS; ++r) p.peer_inbox[r] = ctx->peer_inbox[r];
     p.keep_v = (ctx->l2_keep && n * 8 <= S_KEEP_BYTES) ? 1 : 0;
@@ -320,6 +325,12 @@ extern "C" int pmc_peer_connect(pmc_ctx *ctx, const void *handles) {
         ctx->peer_inbox[r] = static_cast<uint64_t *>(ptr);
     }
     ctx->peer_size = size;
+    // Start the step numbering afresh on every rank: ranks that ran different numbers of (local) sweeps before
+    // connecting would otherwise post mismatching flags forever.  Packets of those earlier sweeps are wiped.
+    PMC_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->sweep_box)
+        PMC_CHECK_CUDA(cudaMemset(ctx->sweep_box, 0, (size_t)2 * ctx->sm_count * 2 * sizeof(uint64_t)));
+    ctx->sweep_seq = 0;
     return PMC_OK;
 }
 

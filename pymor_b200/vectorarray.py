@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from pymor_b200 import _lib
-from pymor_b200._lib import PMC_FORCE_SIMPLE, PMC_SYMMETRIC, PMC_SYNC
+from pymor_b200._lib import PMC_FORCE_SIMPLE, PMC_LOCAL_ONLY, PMC_SYMMETRIC, PMC_SYNC
 from pymor_b200.dist import SingleRank, merge_amax, partition
 from pymor_b200.interface import VectorArray, VectorArrayImpl, VectorSpace, create_random_values
 
@@ -269,15 +269,12 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         drop = {i % self._len for i in _columns(ind, self._len)} if self._len else set()
         keep = [c for c in range(self._len) if c not in drop]
         ctx, pos = self.space.ctx, 0
-        # in-place compaction; a run is moved in chunks no longer than its shift so that source and
-        # destination columns of one launch never overlap
+        # in-place compaction: one launch per run of kept columns (the kernel walks the columns of a run in
+        # increasing order row by row, so overlapping source / destination ranges are safe)
         for start, count in _consecutive_runs(keep):
             shift = start - pos
             if shift and self.n:
-                for off in range(0, count, shift):
-                    c = min(shift, count - off)
-                    ctx.call('pmc_copy', self._ptr(pos + off), self.ld, self._ptr(start + off), self.ld,
-                             c, self.n, 0)
+                ctx.call('pmc_shift_cols', self._ptr(0), self.ld, start, count, shift, self.n, 0)
             pos += count
         self._len = len(keep)
 
@@ -523,7 +520,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         out = ctx.host_f64(nq + 2)
         zp, zcs = (weighted._ptr(start), weighted.ld) if weighted is not None and weight_ptr else (0, 0)
         ctx.call('pmc_mgs_sweep', self._ptr(start), self.ld, zp, zcs, nq, self._ptr(col), self.n, weight_ptr,
-                 out.data_ptr(), PMC_SYNC)
+                 out.data_ptr(), PMC_SYNC | (PMC_LOCAL_ONLY if sp.comm.size == 1 else 0))
         res = out[:nq + 2].numpy().copy()
         if res[nq + 1] != 0.0:
             raise _lib.PmcError('pmc_mgs_sweep: a wait inside the kernel timed out (ranks out of step?)')
@@ -555,9 +552,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         if m == 0 or self.n == 0:
             return new
         ldc = max(_round_up(k, 2), 2)
-        host = np.zeros((ldc, m), dtype=np.float64, order='F')
-        host[:k] = coefficients
-        ct = torch.from_numpy(host.T).to(self.space.device)      # (m, ldc) C-order = F-ordered (ldc, m)
+        ct = self.space.ctx.upload_coefficients(coefficients, k, m, ldc)   # (m, ldc) C-order = F-ordered (ldc, m)
         self.space.ctx.call('pmc_lincomb', pa, csa, k, self.n, ct.data_ptr(), ldc, m, new._ptr(0), new.ld,
                             self.space.kernel_flags)
         # `ct` is released in stream order by torch's caching allocator (same stream as the kernel)

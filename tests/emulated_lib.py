@@ -255,6 +255,12 @@ class EmulatedLib:
             _col(Y, csY, c, nrows)[:] = y[:, c]
         return PMC_OK
 
+    def pmc_shift_cols(self, ctx, A, cs, first, count, shift, n, flags):
+        self._note('pmc_shift_cols')
+        for c in range(first, first + count):                 # increasing order: overlapping ranges are fine
+            _col(A, cs, c - shift, n)[:] = _col(A, cs, c, n)
+        return PMC_OK
+
     def pmc_gather_rows(self, ctx, A, csA, k, n, idx, nidx, out, flags):
         self._note('pmc_gather_rows')
         ix = _vec(idx, nidx, np.int64)

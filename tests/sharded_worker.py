@@ -139,6 +139,17 @@ def main():
         np.testing.assert_allclose(op.apply2(VV, UU), V.T @ (M @ U), atol=1e-11)
         np.testing.assert_allclose(op.pairwise_apply2(VV, UU[:kv]), O.pairwise_inner(V, U[:, :kv], M), atol=1e-11)
         np.testing.assert_allclose(alg.project(op, VV, UU, product=prod).matrix, O.project(M, V, U, P), atol=1e-11)
+        # per-rank construction: every rank hands over ITS row block only (global column numbers); the ghost map is
+        # derived from the column indices -- no rank holds the global matrix
+        lo, hi = sp.offset, sp.offset + sp.local_dim
+        loc = CudaCsrOperator.from_local_rows(M[lo:hi], sp)
+        np.testing.assert_allclose(loc.apply(UU).to_numpy(), M @ U, atol=1e-12)
+        np.testing.assert_allclose(loc.apply2(VV, UU), V.T @ (M @ U), atol=1e-11)
+        locP = CudaCsrOperator.from_local_rows(P[lo:hi], sp, symmetric=True)
+        np.testing.assert_allclose(locP.apply2(UU, UU), U.T @ (P @ U), atol=1e-11)
+        np.testing.assert_allclose(locP.apply_adjoint(VV).to_numpy(), P @ V, atol=1e-12)
+        np.testing.assert_allclose(UU.norm(locP), O.norm(U, P), atol=1e-12)
+        np.testing.assert_allclose(locP.apply_inverse(locP.apply(UU)).to_numpy(), U, atol=1e-7)
         if True:
             # block CG with the halo-exchanging SpMM: Riesz representatives on row-sharded arrays
             import scipy.sparse.linalg as spla
