@@ -48,6 +48,8 @@ def parse_args(argv):
     ap.add_argument('--c5', default='auto', choices=['auto', 'on', 'off'],
                     help="secondary block: BASELINE config 5, project() of a 5-point CSR operator onto 2000 basis vectors, "
                          "6.25M DOF per GPU (50M at 8 GPUs); auto = at 8 GPUs")
+    ap.add_argument('--no-csr-pod', action='store_true',
+                    help='N = 1: skip the secondary block "POD with a CSR (tridiagonal FEM mass matrix) product"')
     ap.add_argument('--accelerate', action='store_true',
                     help='also time pod() with pymor_b200.accelerate_pymor() active (extra key, never the headline)')
     return ap.parse_args(argv)
@@ -415,6 +417,15 @@ def run_cuda(args):
     del prod, w, space
     torch.cuda.empty_cache()
 
+    # ---- N = 1: the same POD with a CSR mass-matrix product (north star: "diagonal or CSR mass-matrix weight") ----
+    csr_pod = None
+    if world == 1 and not args.no_csr_pod:
+        try:
+            csr_pod = csr_weighted_pod(args, make_problem, timed_loop, pod_step)
+        except Exception as exc:
+            csr_pod = {'value': None, 'error': f'{type(exc).__name__}: {exc}'}
+        torch.cuda.empty_cache()
+
     # ---- N > 1: the weak-scaling figure next to the strong one ---------------------------------------------
     weak = None
     if world > 1 and args.scaling == 'strong' and not args.no_weak:
@@ -460,7 +471,7 @@ def run_cuda(args):
                           'device_tflops_excl_host_eigh': flop_global / ((t_step - eigh_mean) * 1e-3) * 1e-12,
                           'host_blas_threads_per_rank': host_threads()},
             'roofline': roofline, 'parity': parity, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'weak': weak,
-            'secondary': None, 'accelerated': accelerated, 'gpu_launches': int(launches), 'clocks': clocks,
+            'secondary': {'pod_csr_product': csr_pod} if csr_pod else None, 'accelerated': accelerated, 'gpu_launches': int(launches), 'clocks': clocks,
         }
 
     # ---- secondary: BASELINE config 5 (RB projection V^T A V, 50M DOF x 2000 basis at 8 GPUs) ---------------
@@ -485,11 +496,48 @@ def run_cuda(args):
             result = {'error': f'{type(exc).__name__}: {exc}'}
         watchdog.cancel()
         if rank == 0:
-            line['secondary'] = {'projection_c5': result}
+            line['secondary'] = dict(line['secondary'] or {}, projection_c5=result)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def csr_weighted_pod(args, make_problem, timed_loop, pod_step):
+    """pod(A, product=M, method='method_of_snapshots') with M the 1-D FEM mass matrix h/6 [1 4 1] as a device CSR
+    operator: the weighted Gramians run as the fused CSR two-form -- row panels of M A contracted by
+    the tensor-core kernel on the lower tile triangle only (M is symmetric), no n x k temporary."""
+    import scipy.sparse as sps
+
+    from pymor_b200.operators import CudaCsrOperator
+    space, A, w, prod = make_problem(args.n, seed=44)
+    del w, prod
+    n, k = space.dim, args.k
+    h = 1.0 / (n + 1)
+    M = sps.diags([np.full(n - 1, h / 6), np.full(n, 4 * h / 6), np.full(n - 1, h / 6)], [-1, 0, 1], format='csr')
+    op = CudaCsrOperator.from_local_rows(M, space, symmetric=True)
+    nnz = M.nnz
+    del M
+    A.scal(1.0 / np.sqrt(h))                                   # ||a_j||_M = O(1) like in the diagonal case
+
+    def step():
+        U, s = pod_step(A, op)
+        mm = len(U)
+        del U
+        return mm
+
+    step(); step()
+    times, m = timed_loop(step, 3)
+    t = float(np.mean(times))
+    U, s = pod_step(A, op)
+    orth = float(np.max(np.abs(U.gramian(op) - np.eye(len(U)))))
+    trace = float(np.sum(A.norm2(op)))
+    flop = n * k * (k + 1.0) + 2.0 * n * k * m + n * m * (m + 1.0) + 2.0 * nnz * (k + m)
+    return {'value': flop / (t * 1e-3) * 1e-12, 'unit': 'TFLOP/s', 'ms_per_step': t, 'steps': 3, 'modes_kept': int(m),
+            'workload': f'pymor pod(method_of_snapshots) of {n} x {k}, product = CSR tridiagonal FEM mass matrix ({nnz} nnz)',
+            'algorithmic_flop': flop,
+            'parity': {'orth_err_max_abs(U^T M U - I)': orth,
+                       'trace_identity_rel_err': float(abs(np.sum(s ** 2) - trace) / trace)}}
 
 
 def parity_block(args, space, A, w, prod, comm, device, pod_step):

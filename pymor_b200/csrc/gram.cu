@@ -331,7 +331,7 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
         } else {
             tmW = tmA;
         }
-        if ((p.opts & G2_OPT_ENABLE) && p.symmetric != 2) {
+        if (p.opts & G2_OPT_ENABLE) {
             // second-generation tile kernel with its own reduction (gram2.cu)
             rc = pmc_gram2_launch(ctx, tmA, tmB, tmW, p, items, nsplit, w != nullptr, out, ldo, accumulate);
             if (rc) return rc;

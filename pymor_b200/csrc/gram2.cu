@@ -40,28 +40,43 @@ constexpr size_t GRAM2_SMEM = 1024 /*align slack*/ + (size_t)STAGES * (2 * TILE_
 
 // One stage (16 rows = KS quarter-steps of 4) of a warp's block.  NM x NN sub-blocks of 8x8; TRI keeps
 // the sub-blocks with ni <= mi.  `fo` holds the fragment offsets of the warp's quarter-steps.
-// WREG: the diagonal weight of the fragment's row (w_s[wo[ks]]) multiplies the B fragments in registers.
-template <int NM, int NN, bool TRI, int KS, bool WREG>
+// WREG != 0: the diagonal weight of the fragment's row (w_s[wo[ks]]) multiplies the B fragments in registers
+// (fl(w * b) first, exactly as gram_dmma_kernel rounds).  WREG == 2 additionally loads the stage's weights up front
+// and issues the DMMAs column-of-sub-blocks by column (ni-major): the first NM of them need only b[0], so the DMULs
+// of b[1..] -- which queue behind DMMAs on the shared FP64 pipe -- are off the critical path.
+template <int NM, int NN, bool TRI, int KS, int WREG>
 __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *a_s, const double *b_s,
                                           const int (&fo)[4], const double *w_s, const int (&wo)[4]) {
+    double wv[KS];
+    if (WREG == 2) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) wv[ks] = w_s[wo[ks]];
+    }
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         double a[NM], b[NN];
 #pragma unroll
-        for (int mi = 0; mi < NM; ++mi) a[mi] = a_s[mi * 8 * BK + fo[ks]];
-#pragma unroll
         for (int ni = 0; ni < NN; ++ni) b[ni] = b_s[ni * 8 * BK + fo[ks]];
+#pragma unroll
+        for (int mi = 0; mi < NM; ++mi) a[mi] = a_s[mi * 8 * BK + fo[ks]];
+        if (WREG == 1) wv[ks] = w_s[wo[ks]];
         if (WREG) {
-            const double wv = w_s[wo[ks]];
-            // fl(w * b) first, exactly as gram_dmma_kernel rounds
 #pragma unroll
-            for (int ni = 0; ni < NN; ++ni) b[ni] *= wv;
+            for (int ni = 0; ni < NN; ++ni) b[ni] *= wv[ks];
         }
-#pragma unroll
-        for (int mi = 0; mi < NM; ++mi)
+        if (WREG == 2) {
 #pragma unroll
             for (int ni = 0; ni < NN; ++ni)
-                if (!TRI || ni <= mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+#pragma unroll
+                for (int mi = 0; mi < NM; ++mi)
+                    if (!TRI || ni <= mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        } else {
+#pragma unroll
+            for (int mi = 0; mi < NM; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NN; ++ni)
+                    if (!TRI || ni <= mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
     }
 }
 
@@ -69,8 +84,8 @@ __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *
 // warp contracts half of the stage (2 quarter-steps), + 32 for a quarter; triangular (diagonal) blocks 48 + nm-1
 constexpr int SHAPE_IDLE = -1, SHAPE_TRI = 48;
 
-// WMODE: 0 no weight, 1 weight applied in shared memory once per stage (ready ring), 2 weight applied to the
-// fragments in registers
+// WMODE: 0 no weight, 1 weight applied in shared memory once per stage (ready ring), 2 / 3 weight applied to the
+// fragments in registers (3: weights of a stage loaded up front, ni-major DMMA order)
 template <int WMODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -85,7 +100,8 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t *empty = full + STAGES;
     uint64_t *ready = empty + STAGES;               // WMODE 1: stage has been scaled by all warps
     constexpr bool WEIGHTED = WMODE != 0;           // the weight tile is loaded
-    constexpr bool WSMEM = WMODE == 1, WREG = WMODE == 2;
+    constexpr bool WSMEM = WMODE == 1;
+    constexpr int WREG = WMODE == 2 ? 1 : WMODE == 3 ? 2 : 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -93,7 +109,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tile = item % p.ntiles, split = item / p.ntiles;
     int ti, tj;
     decode_tile(p, tile, ti, tj);
-    const bool diag = p.symmetric && ti == tj;
+    const bool diag = p.symmetric == 1 && ti == tj;   // (symmetric == 2: lower tiles of a general product, two operands)
     const int64_t r0 = (int64_t)split * p.rows_per_split;
     const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
     const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
@@ -237,8 +253,8 @@ __global__ void gram2_reduce_kernel(const double *__restrict__ partials, int nsp
     const int il = e % BM, jl = e / BM;
     const int gi = ti * BM + il, gj = tj * BN + jl;
     if (gi >= p.kA || gj >= p.kB) return;
-    const bool diag = p.symmetric && ti == tj;
-    if (diag && gi < gj) return;                    // strictly-upper part of diagonal tiles: mirrored
+    const bool diag = p.symmetric == 1 && ti == tj;
+    if (p.symmetric && ti == tj && gi < gj) return; // strictly-upper part of diagonal tiles: mirrored
     const size_t tile_elems = (size_t)BM * BN;
     const double *src = partials + (size_t)tile * tile_elems;
     const size_t step = (size_t)p.ntiles * tile_elems;
@@ -284,6 +300,10 @@ int pmc_gram2_launch(pmc_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tm
         PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)GRAM2_SMEM));
         gram2_dmma_kernel<1><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+    } else if (weighted && (p.opts & G2_OPT_W_NIMAJOR)) {
+        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)GRAM2_SMEM));
+        gram2_dmma_kernel<3><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
     } else if (weighted) {
         PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)GRAM2_SMEM));

@@ -96,7 +96,8 @@ def _block_error_map(G, G_ref, scale):
         return f'max scaled error per 32x32 block (rows = block row i, 4 blocks = one 128 tile):\n{m}'
 
 
-@pytest.mark.parametrize('opts', [16, 16 | 32, 16 | 64, 16 | 128, 16 | 32 | 64 | 128, 16 | 256, 16 | 64 | 256])
+@pytest.mark.parametrize('opts', [16, 16 | 32, 16 | 64, 16 | 128, 16 | 32 | 64 | 128, 16 | 256, 16 | 64 | 256, 16 | 512,
+                                  16 | 64 | 512])
 def test_gram2_variant_parity(loaded_lib, rng, opts):
     from pymor_b200._lib import get_context
     from pymor_b200.operators import CudaDiagonalOperator
@@ -376,6 +377,14 @@ def test_csr_pairwise_and_symmetric_twoform(loaded_lib, rng):
         np.testing.assert_array_equal(loc.apply(UU[:3]).to_numpy(), op.apply(UU[:3]).to_numpy())
         G2 = op.apply2(VV, UU)                                            # general pair: full product
         assert O.gram_rel_error(G2, V.T @ MU, V, MU) < GRAM_TOL
+        if dim == 60000:                                                  # the first-generation tile kernel as well
+            sp.ctx.set_option('gram_opts', 0)
+            try:
+                G1 = op.apply2(UU, UU)
+            finally:
+                sp.ctx.set_option('gram_opts', 16)
+            assert O.gram_rel_error(G1, U.T @ MU, U, MU) < GRAM_TOL
+            np.testing.assert_array_equal(G1, G1.T)
 
 
 @pytest.mark.parametrize('dim', [1, 7, 1001, 40000])
