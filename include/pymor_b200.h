@@ -228,6 +228,19 @@ int pmc_csr_pairwise(pmc_ctx *ctx, int64_t nrows, const int64_t *rowptr, const i
                      const double *vals, const double *V, int64_t csV, const double *U, int64_t csU,
                      const double *ghost, int32_t k, double *out, uint32_t flags);
 
+/* Collectives of the row-sharded arrays (one process per GPU on one box).  The reference gathers the per-rank
+ * partial results on rank 0 and sums them on the host (vectorarrays/mpi.py:394-416, MPI Gather of pickled arrays);
+ * here every rank holds its k1 x k2 (or k) partial in device memory and pmc_allreduce_sum adds them in place over
+ * NVLink (ncclAllReduce, fp64, on the context's stream, i.e. ordered behind the reduction kernel that wrote `buf`).
+ * NCCL is looked up in the process at run time (no link-time dependency).  pmc_comm_unique_id: 128 bytes created by
+ * one rank, to be handed to all ranks by the host; pmc_comm_init is collective over the `size` ranks. */
+#define PMC_COMM_ID_BYTES 128
+int pmc_comm_unique_id(void *id_out);
+int pmc_comm_init(pmc_ctx *ctx, int rank, int size, const void *id_bytes);
+int pmc_comm_destroy(pmc_ctx *ctx);
+int pmc_comm_size(pmc_ctx *ctx); /* 0 without a communicator */
+int pmc_allreduce_sum(pmc_ctx *ctx, double *buf, int64_t count, uint32_t flags);
+
 /* Roofline denominators measured on the spot: sustained FP64 tensor-core (DMMA) and DFMA
  * throughput in TFLOP/s over `ms` milliseconds of back-to-back issue on every SM.  use_dmma: 0 = DFMA, 1 = DMMA,
  * 2 = half of the warps DMMA / half DFMA, 3 = every warp interleaves both (2 and 3 report the combined rate: do the

@@ -22,6 +22,7 @@ PMC_LOWER_ONLY = 8
 PMC_LOCAL_ONLY = 16
 PMC_MAX_PEERS = 8
 PMC_IPC_HANDLE_BYTES = 64
+PMC_COMM_ID_BYTES = 128
 
 LIB_PATH = Path(__file__).resolve().parent / 'lib' / 'libpymor_b200.so'
 
@@ -53,6 +54,9 @@ _CTX_FUNCS = {
     'pmc_peer_create': [c_int, c_int, _P],
     'pmc_peer_connect': [_P],
     'pmc_peer_destroy': [],
+    'pmc_comm_init': [c_int, c_int, _P],
+    'pmc_comm_destroy': [],
+    'pmc_allreduce_sum': [_P, _I64, _U32],
     'pmc_ctx_set_option': [ctypes.c_char_p, c_int],
     'pmc_ctx_get_option': [ctypes.c_char_p, ctypes.POINTER(c_int)],
     'pmc_ctx_kernel_times': [_P, _P, _I32, ctypes.POINTER(_I32)],
@@ -67,6 +71,8 @@ _OTHER_FUNCS = {
     'pmc_ctx_sync': ([_P], c_int),
     'pmc_ctx_sm_count': ([_P], c_int),
     'pmc_ctx_launch_count': ([_P], c_int64),
+    'pmc_comm_unique_id': ([_P], c_int),
+    'pmc_comm_size': ([_P], c_int),
 }
 EXPORTED_SYMBOLS = sorted(list(_CTX_FUNCS) + list(_OTHER_FUNCS))
 
@@ -137,6 +143,7 @@ class DeviceContext:
         self._copy_stream = None
         self.pending = None
         self._peer_comm = None
+        self._native_comm = None                       # (rank, size) of the library-side NCCL communicator
         self.fuse_axpy = os.environ.get('PMC_NO_FUSE_AXPY', '0') != '1'
         self.scalar = np.zeros(1)                      # staging for scalar coefficients (read at launch)
         self.scalar_ptr = self.scalar.ctypes.data
@@ -278,6 +285,35 @@ class DeviceContext:
         self.call('pmc_peer_connect', ctypes.cast(table, _P))
         comm.barrier()                 # nobody posts before everybody has connected
         self._peer_comm = comm
+
+    def attach_comm(self, comm):
+        """Give the library its own NCCL communicator over the ranks of ``comm`` (collective; the 128-byte NCCL id is
+        created by rank 0 and handed round through ``comm``).  Afterwards :meth:`allreduce_sum` adds device buffers
+        in place on the library's stream.  Returns whether the native path is in place on ALL ranks."""
+        if self._native_comm is not None:
+            return self._native_comm == (comm.rank, comm.size)
+        ident = None
+        if comm.rank == 0:
+            buf = ctypes.create_string_buffer(PMC_COMM_ID_BYTES)
+            if self.lib.pmc_comm_unique_id(ctypes.cast(buf, _P)) == PMC_OK:
+                ident = buf.raw
+        ident = comm.broadcast_object(ident)
+        ok = False
+        if ident is not None:
+            buf = ctypes.create_string_buffer(ident, PMC_COMM_ID_BYTES)
+            ok = self.lib.pmc_comm_init(self.handle, comm.rank, comm.size, ctypes.cast(buf, _P)) == PMC_OK
+        ok = all(comm.allgather_object(bool(ok)))
+        if not ok:
+            self.lib.pmc_comm_destroy(self.handle)
+            return False
+        self._native_comm = (comm.rank, comm.size)
+        return True
+
+    def allreduce_sum(self, tensor):
+        """In-place sum of a device fp64 tensor over the ranks of the attached communicator (ncclAllReduce on the
+        library's stream, ordered behind the kernel that produced the data)."""
+        self.call('pmc_allreduce_sum', tensor.data_ptr(), tensor.numel(), 0)
+        return tensor
 
     def set_option(self, name, value):
         """Kernel tuning switch (``gram_opts``, ``gram_waves``, ``csr_variant``, ``l2_keep``)."""

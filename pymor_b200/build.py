@@ -17,7 +17,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / 'csrc'
 LIB_DIR = PKG_DIR / 'lib'
 LIB_PATH = LIB_DIR / 'libpymor_b200.so'
-SOURCES = ['ctx.cu', 'blas1.cu', 'mgs.cu', 'gram.cu', 'gram2.cu', 'lincomb.cu', 'csr.cu', 'peak.cu']
+SOURCES = ['ctx.cu', 'blas1.cu', 'mgs.cu', 'gram.cu', 'gram2.cu', 'lincomb.cu', 'csr.cu', 'comm.cu', 'peak.cu']
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17', '-lineinfo',
@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed, see output above')
-    cmd = [nvcc, '-shared', '-o', str(LIB_PATH), *objs, '-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [nvcc, '-shared', '-o', str(LIB_PATH), *objs, '-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
     subprocess.run(cmd, check=True)
     stamp.write_text(digest)
     return LIB_PATH

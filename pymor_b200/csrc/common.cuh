@@ -38,6 +38,9 @@ struct pmc_ctx {
     int peer_rank, peer_size, peer_pending_size;
     uint64_t *peer_inbox_local;
     uint64_t *peer_inbox[PMC_MAX_PEERS];
+    // NCCL communicator of the row-sharded arrays (comm.cu); NULL: single GPU or collectives done by the host
+    void *nccl_comm;
+    int comm_rank, comm_size;
     // per-launch kernel times (option "kernel_timing"): event pairs around the launches of the hot kernels
     int kernel_timing;
     int t_count;

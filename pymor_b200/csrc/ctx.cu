@@ -75,6 +75,7 @@ extern "C" int pmc_ctx_destroy(pmc_ctx *ctx) {
     if (!ctx) return PMC_OK;
     cudaSetDevice(ctx->device);
     pmc_peer_destroy(ctx);
+    pmc_comm_destroy(ctx);
     for (int i = 0; i < PMC_TIMING_SLOTS; ++i)
         for (int j = 0; j < 2; ++j)
             if (ctx->t_ev[i][j]) cudaEventDestroy(ctx->t_ev[i][j]);

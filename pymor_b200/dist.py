@@ -10,6 +10,8 @@ and take identical control-flow decisions in ``gram_schmidt`` / ``pod``.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -32,6 +34,12 @@ class SingleRank:
     def allgather_object(self, obj):
         return [obj]
 
+    def broadcast_object(self, obj, src=0):
+        return obj
+
+    def attach(self, ctx):
+        pass
+
     def exchange(self, sends, recvs):
         assert not sends and not recvs
 
@@ -51,10 +59,32 @@ class ProcessGroupComm:
         self.group = group
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
+        self._native = {}            # DeviceContext -> whether the library-side NCCL communicator is in place
+
+    def attach(self, ctx):
+        """Collective, called once per (communicator, device context) by ``CudaVectorSpace``: let the LIBRARY own
+        the all-reduce of the k x k / k partials (``pmc_allreduce_sum``: NCCL behind the C ABI, on the library's
+        stream) instead of ``torch.distributed``.  Opt-in with ``PMC_NATIVE_COMM=1`` (default: the collectives stay in
+        ``torch.distributed``); the gloo process groups of the CPU tests always use ``torch.distributed``."""
+        if ctx in self._native:
+            return
+        use = (os.environ.get('PMC_NATIVE_COMM', '0') == '1' and ctx.device.type == 'cuda'
+               and dist.get_backend(self.group) == 'nccl' and hasattr(ctx.lib, 'pmc_allreduce_sum'))
+        self._native[ctx] = bool(use) and ctx.attach_comm(self)
 
     def allreduce_sum_(self, tensor):
+        if tensor.is_cuda and tensor.dtype == torch.float64 and tensor.is_contiguous():
+            for ctx, native in self._native.items():
+                if native and ctx.device == tensor.device:
+                    return ctx.allreduce_sum(tensor)
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
         return tensor
+
+    def broadcast_object(self, obj, src=0):
+        box = [obj]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
+                                   group=self.group)
+        return box[0]
 
     def allgather(self, tensor):
         out = [torch.empty_like(tensor) for _ in range(self.size)]

@@ -664,6 +664,7 @@ class CudaVectorSpace(VectorSpace):
             device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else 'cuda'
         self._ctx = _lib.get_context(device)           # raises without library / device
         self.device = self._ctx.device
+        self._comm.attach(self._ctx)                   # collective: NCCL communicator behind the C ABI (dist.py)
         dims, offsets = partition(self.dim, self._comm.size)
         self._local_dims = dims
         self._local_dim = int(dims[self._comm.rank])
