@@ -69,7 +69,8 @@ int pmc_ctx_sm_count(pmc_ctx *ctx);
 int64_t pmc_ctx_launch_count(pmc_ctx *ctx);
 /* Tuning switches of the kernels (defaults come from the environment when the context is created):
  * "gram_opts" (bit set of pymor_b200/csrc/gram2_plan.h; 16 selects the second-generation Gram tile kernel),
- * "gram_waves" (target CTA waves of the split-n Gram kernel), "csr_variant", "l2_keep".  No reference
+ * "gram_waves" (target CTA waves of the split-n Gram kernel), "gram_l2_mb" (L2 budget that bounds the rows per split),
+ * "csr_variant", "l2_keep", "kernel_timing".  No reference
  * counterpart; results do not depend on them beyond the summation order of the Gram partials. */
 int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value);
 int pmc_ctx_get_option(pmc_ctx *ctx, const char *name, int *value);

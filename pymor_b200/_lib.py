@@ -172,7 +172,7 @@ class DeviceContext:
         rc = fn(self.handle, *args)
         if rc == PMC_ERR_WORKSPACE:
             need = int(self.lib.pmc_ctx_workspace_needed(self.handle))
-            self.ensure_workspace(need + (need >> 2))
+            self.ensure_workspace(need + min(need >> 2, 64 << 20))
             rc = fn(self.handle, *args)
         if rc != PMC_OK:
             raise PmcError(f'{name} failed ({rc}): {self._err()}')

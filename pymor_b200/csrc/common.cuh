@@ -29,6 +29,7 @@ struct pmc_ctx {
     void *encode_tiled;      // cuTensorMapEncodeTiled entry point
     int csr_variant;         // 0 = row-per-thread SpMM (default; 3.4 TB/s on the 5-point stencil), 1 = row-tile variant (slower, kept for A/B)
     int gram_waves;          // target number of CTA waves of the split-n Gram kernel (env PMC_GRAM_WAVES)
+    int gram_l2_mb;          // L2 budget (MB) for the rows shared by the tiles of the splits in flight; 0: split by waves only
     int gram_opts;           // ablation switches for gram_dmma_kernel (env PMC_GRAM_OPTS)
     int l2_keep;             // keep single hot vectors L2-resident (env PMC_NO_L2_KEEP=1 disables)
     // Gram-Schmidt sweep kernel (mgs.cu): flagged CTA packets, abort flag, step counter; peer inboxes

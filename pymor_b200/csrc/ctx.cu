@@ -67,6 +67,8 @@ extern "C" int pmc_ctx_create(int device, void *stream, pmc_ctx **out) {
     c->csr_variant = cv ? atoi(cv) : 0;
     const char *gw = getenv("PMC_GRAM_WAVES");
     c->gram_waves = (gw && atoi(gw) > 0) ? atoi(gw) : 32;
+    const char *gl = getenv("PMC_GRAM_L2_MB");
+    c->gram_l2_mb = gl ? atoi(gl) : 48;
     *out = c;
     return PMC_OK;
 }
@@ -108,6 +110,7 @@ static int *pmc_option_slot(pmc_ctx *ctx, const char *name) {
     if (!ctx || !name) return nullptr;
     if (!strcmp(name, "gram_opts")) return &ctx->gram_opts;
     if (!strcmp(name, "gram_waves")) return &ctx->gram_waves;
+    if (!strcmp(name, "gram_l2_mb")) return &ctx->gram_l2_mb;
     if (!strcmp(name, "csr_variant")) return &ctx->csr_variant;
     if (!strcmp(name, "l2_keep")) return &ctx->l2_keep;
     if (!strcmp(name, "kernel_timing")) return &ctx->kernel_timing;
@@ -116,7 +119,7 @@ static int *pmc_option_slot(pmc_ctx *ctx, const char *name) {
 
 extern "C" int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value) {
     int *slot = pmc_option_slot(ctx, name);
-    PMC_REQUIRE(slot != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep, kernel_timing)");
+    PMC_REQUIRE(slot != nullptr, "unknown option (gram_opts, gram_waves, gram_l2_mb, csr_variant, l2_keep, kernel_timing)");
     PMC_REQUIRE(slot != &ctx->gram_waves || value > 0, "gram_waves must be positive");
     *slot = value;
     return PMC_OK;
@@ -124,7 +127,7 @@ extern "C" int pmc_ctx_set_option(pmc_ctx *ctx, const char *name, int value) {
 
 extern "C" int pmc_ctx_get_option(pmc_ctx *ctx, const char *name, int *value) {
     int *slot = pmc_option_slot(ctx, name);
-    PMC_REQUIRE(slot != nullptr && value != nullptr, "unknown option (gram_opts, gram_waves, csr_variant, l2_keep, kernel_timing)");
+    PMC_REQUIRE(slot != nullptr && value != nullptr, "unknown option (gram_opts, gram_waves, gram_l2_mb, csr_variant, l2_keep, kernel_timing)");
     *value = *slot;
     return PMC_OK;
 }

@@ -297,6 +297,23 @@ int pmc_gram_impl(pmc_ctx *ctx, const double *A, int64_t csA, int32_t kA, const 
     // items differ in cost (diagonal SYRK tiles are cheaper), so the tail of the last wave matters:
     // more, smaller items keep it short (env PMC_GRAM_WAVES for tuning)
     int64_t nsplit = ceil_div64((int64_t)ctx->gram_waves * ctas_per_wave, p.ntiles);
+    // ... and SHORT items keep the operands in L2.  The CTAs that contract the same rows (all tiles of one split)
+    // are dispatched one after the other as SMs become free, i.e. staggered by ~0.2 item durations in steady state;
+    // the rows the first of them has read must still be in the 126 MB L2 when the last one arrives, for every split
+    // in flight (ctas_per_wave / ntiles of them).  Measured at 10M x 1000 (profiles/r02_summary.md): 32 waves of
+    // items -> 453 GB read from DRAM for 80 GB of operands, 256 waves -> 188 GB at the same kernel time.
+    if (tma_ok && ctx->gram_l2_mb > 0) {
+        const double row_bytes = 8.0 * (sym ? kA : kA + kB);                    // distinct operand bytes per row
+        const double in_flight = (double)ctas_per_wave / p.ntiles;              // splits being contracted at a time
+        double rows = (double)ctx->gram_l2_mb * 1e6 / (0.2 * row_bytes * (in_flight > 1.0 ? in_flight : 1.0));
+        if (rows < 64.0 * rows_q) rows = 64.0 * rows_q;
+        const int64_t by_l2 = ceil_div64(n, (int64_t)rows);
+        // the partial tiles must stay small next to the operands (5 %, and within 4 GB)
+        const double ws_limit = 4e9 < 0.05 * row_bytes * n ? 4e9 : 0.05 * row_bytes * n;
+        const int64_t by_ws = (int64_t)(ws_limit / ((double)p.ntiles * T * T * 8.0));
+        int64_t want = by_l2 < by_ws ? by_l2 : by_ws;
+        if (want > nsplit) nsplit = want;
+    }
     const int64_t max_split = steps / 64 > 0 ? steps / 64 : 1;
     if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;

@@ -70,7 +70,7 @@ class EmulatedLib:
         return self.launches
 
     def pmc_ctx_set_option(self, ctx, name, value):
-        if name not in (b'gram_opts', b'gram_waves', b'csr_variant', b'l2_keep', b'kernel_timing'):
+        if name not in (b'gram_opts', b'gram_waves', b'gram_l2_mb', b'csr_variant', b'l2_keep', b'kernel_timing'):
             self._err = b'unknown option'
             return PMC_ERR_INVALID
         self.options = getattr(self, 'options', {})

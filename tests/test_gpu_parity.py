@@ -335,8 +335,10 @@ def test_csr_twoform_multi_panel(loaded_lib, rng):
     """CSR two-form across several row panels (the fused V^T (M U) path) vs SciPy."""
     from pymor_b200.operators import CudaCsrOperator
     dim, kv, ku = 60000, 40, 600          # 600 columns -> ~10k-row panels -> 6 panels
+    nz = dim
     M = (sps.diags([-np.ones(dim - 1), 2.5 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1])
-         + sps.random(dim, dim, density=2e-5, random_state=3)).tocsr()
+         + sps.coo_matrix((rng.standard_normal(nz), (rng.integers(0, dim, nz), rng.integers(0, dim, nz))),
+                          shape=(dim, dim))).tocsr()
     sp = space_of(dim)
     V, U = rng.standard_normal((dim, kv)), rng.standard_normal((dim, ku))
     op = CudaCsrOperator(M, sp)
@@ -354,7 +356,10 @@ def test_csr_pairwise_and_symmetric_twoform(loaded_lib, rng):
     for dim, k in ((1, 3), (777, 5), (60000, 300), (400003, 130)):
         M = (sps.diags([-np.ones(dim - 1), 2.5 * np.ones(dim), -np.ones(dim - 1)], [-1, 0, 1])).tocsr()
         if dim > 1000:
-            R = sps.random(dim, dim, density=2e-5, random_state=3)
+            # (sps.random draws without replacement from dim^2 candidates: terabytes at this size)
+            nz = 4 * dim
+            R = sps.coo_matrix((rng.standard_normal(nz), (rng.integers(0, dim, nz), rng.integers(0, dim, nz))),
+                               shape=(dim, dim))
             M = (M + R + R.T).tocsr()                                  # symmetric, irregular rows
         sp = space_of(dim)
         V, U = rng.standard_normal((dim, k)), rng.standard_normal((dim, k))
