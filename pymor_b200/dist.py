@@ -64,11 +64,12 @@ class ProcessGroupComm:
     def attach(self, ctx):
         """Collective, called once per (communicator, device context) by ``CudaVectorSpace``: let the LIBRARY own
         the all-reduce of the k x k / k partials (``pmc_allreduce_sum``: NCCL behind the C ABI, on the library's
-        stream) instead of ``torch.distributed``.  Opt-in with ``PMC_NATIVE_COMM=1`` (default: the collectives stay in
-        ``torch.distributed``); the gloo process groups of the CPU tests always use ``torch.distributed``."""
+        stream) instead of ``torch.distributed`` (which stays the bootstrap channel for the NCCL id and carries the
+        halo exchange).  ``PMC_NATIVE_COMM=0`` keeps the all-reduce in ``torch.distributed`` as well; the gloo process
+        groups of the CPU tests always do."""
         if ctx in self._native:
             return
-        use = (os.environ.get('PMC_NATIVE_COMM', '0') == '1' and ctx.device.type == 'cuda'
+        use = (os.environ.get('PMC_NATIVE_COMM', '1') != '0' and ctx.device.type == 'cuda'
                and dist.get_backend(self.group) == 'nccl' and hasattr(ctx.lib, 'pmc_allreduce_sum'))
         self._native[ctx] = bool(use) and ctx.attach_comm(self)
 

@@ -11,7 +11,7 @@ QUICK=${QUICK:-0}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 show() { for f in "$@"; do grep -hE '^\{' "$f" 2>/dev/null | cut -c1-${W:-700}; done; }
 { nproc; free -g | head -2; nvidia-smi topo -m | head -12; numactl -H 2>/dev/null | head -8; lscpu | grep -E "NUMA|Model name|Socket" ; } > $O/r02_multi_info_${N}gpu.txt 2>&1
-timeout 900 $TR tests/sharded_worker.py --real > $O/r02_sharded_worker_${N}gpu.log 2>&1; echo "exit $?" >> $O/r02_sharded_worker_${N}gpu.log
+PMC_NATIVE_COMM=0 timeout 900 $TR tests/sharded_worker.py --real > $O/r02_sharded_worker_${N}gpu.log 2>&1; echo "exit $?" >> $O/r02_sharded_worker_${N}gpu.log
 tail -n 4 $O/r02_sharded_worker_${N}gpu.log | cut -c1-300
 # the same worker with the library-side NCCL communicator (pmc_allreduce_sum) instead of torch.distributed
 PMC_NATIVE_COMM=1 timeout 900 $TR tests/sharded_worker.py --real > $O/r02_sharded_worker_native_${N}gpu.log 2>&1; echo "exit $?" >> $O/r02_sharded_worker_native_${N}gpu.log
@@ -19,9 +19,9 @@ tail -n 3 $O/r02_sharded_worker_native_${N}gpu.log | cut -c1-300
 C5=on; [ "$N" = "8" ] && C5=auto
 timeout 1200 $TR bench.py --gpus $N --steps ${STEPS:-4} --warmup 3 --c5 $C5 --accelerate > $O/r02_bench_${N}gpu.log 2>&1; echo "bench exit $?" >> $O/r02_bench_${N}gpu.log
 W=6000 show $O/r02_bench_${N}gpu.log; tail -n 2 $O/r02_bench_${N}gpu.log | cut -c1-400
-if grep -q "exit 0" $O/r02_sharded_worker_native_${N}gpu.log; then
-    PMC_NATIVE_COMM=1 timeout 600 $TR bench.py --gpus $N --steps ${STEPS:-4} --warmup 3 --c5 off --no-e2e --no-weak > $O/r02_bench_${N}gpu_native.log 2>&1
-    W=1500 show $O/r02_bench_${N}gpu_native.log
+if [ "$QUICK" != "1" ]; then
+    PMC_NATIVE_COMM=0 timeout 600 $TR bench.py --gpus $N --steps ${STEPS:-4} --warmup 3 --c5 off --no-e2e --no-weak > $O/r02_bench_${N}gpu_torchdist.log 2>&1
+    W=1500 show $O/r02_bench_${N}gpu_torchdist.log
 fi
 gs() { tag=$1; shift; timeout 300 $TR tools/bench_gs.py --dofs 10000000 --k 256 "$@" > $O/r02_gs_${N}gpu_${tag}.log 2>&1; show $O/r02_gs_${N}gpu_${tag}.log; }
 gs sweep --sweep
