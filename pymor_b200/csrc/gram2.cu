@@ -84,10 +84,18 @@ __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *
 // warp contracts half of the stage (2 quarter-steps), + 32 for a quarter; triangular (diagonal) blocks 48 + nm-1
 constexpr int SHAPE_IDLE = -1, SHAPE_TRI = 48;
 
-// WMODE: 0 no weight, 1 weight applied in shared memory once per stage (ready ring), 2 / 3 weight applied to the
-// fragments in registers (3: weights of a stage loaded up front, ni-major DMMA order)
+// WMODE: 0 no weight, 1 weight applied in shared memory once per stage by the MMA warps themselves (ready ring),
+// 2 / 3 weight applied to the fragments in registers (3: weights of a stage loaded up front, ni-major DMMA order),
+// 4 weight applied in shared memory by a DEDICATED warpgroup (warp specialisation): warps 16..19 -- one per SMSP --
+// scale the B tile of every stage as soon as it has landed (each element once: 16 DMUL per warp and stage instead
+// of the 64 that register scaling costs every SMSP, and none of it on the MMA warps' instruction streams), the 16
+// MMA warps wait for `ready` instead of `full` and run the unweighted stage loop.  Registers move from the scaler
+// warpgroup to the MMA warpgroups with setmaxnreg (640 threads start at 96; the scaler warpgroup shrinks to 32 and thereby releases exactly the 8192 registers the four MMA warpgroups need to grow to 112).
+constexpr int WS_THREADS = THREADS + 128;
+constexpr int WS_MMA_REGS = 112, WS_SCALER_REGS = 32;
+
 template <int WMODE>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(WMODE == 4 ? WS_THREADS : THREADS, 1)
 gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmW, const GramParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -101,6 +109,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t *ready = empty + STAGES;               // WMODE 1: stage has been scaled by all warps
     constexpr bool WEIGHTED = WMODE != 0;           // the weight tile is loaded
     constexpr bool WSMEM = WMODE == 1;
+    constexpr bool WSPEC = WMODE == 4;              // dedicated scaler warpgroup
     constexpr int WREG = WMODE == 2 ? 1 : WMODE == 3 ? 2 : 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -115,7 +124,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
 
     const int vm = min(BM, p.kA - ti * BM), vn = min(BN, p.kB - tj * BN);   // valid rows / cols of this tile
-    const G2Plan plan = g2_plan(warp, diag, vm, vn, p.opts);
+    const G2Plan plan = g2_plan(warp < G2_WARPS ? warp : 0, diag, vm, vn, p.opts);
     const int shape = !plan.active ? SHAPE_IDLE
                       : plan.tri   ? SHAPE_TRI + plan.nm - 1
                                    : (plan.nm - 1) * 4 + (plan.nn - 1) + (plan.nks == 4 ? 0 : plan.nks == 2 ? 16 : 32);
@@ -127,12 +136,45 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], G2_WARPS);
-            mbar_init(&ready[s], G2_WARPS);
+            mbar_init(&ready[s], WSPEC ? 4 : G2_WARPS);
         }
         fence_barrier_init();
         fence_proxy_async();
     }
     __syncthreads();
+
+    if (WSPEC) {
+        if (warp >= G2_WARPS) {
+            // ---- scaler warpgroup: B tile of stage kt *= w (rows of the stage), written to the B slot -- in place for
+            // off-diagonal tiles, from the A slot for diagonal tiles (which load one operand only)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_SCALER_REGS));
+            const int st = tid - THREADS;                       // 0..127
+            for (int kt = 0; kt < nk; ++kt) {
+                const int s = kt % STAGES;
+                mbar_wait(&full[s], (kt / STAGES) & 1);
+                const double *src = (diag ? sA : sB) + s * TILE_ELEMS;
+                double *dst = sB + s * TILE_ELEMS;
+                const double *wv = sW + s * BK;
+#pragma unroll 2
+                for (int part = 0; part < 8; ++part) {
+                    // 16-byte chunk q of the swizzled tile: column c = q / 8, physical chunk q % 8 holds rows 2j, 2j+1
+                    // with j = (q % 8) ^ (c % 8)
+                    const int q = part * 128 + st;
+                    const int j = (q & 7) ^ ((q >> 3) & 7);
+                    double2 v = *reinterpret_cast<const double2 *>(src + 2 * q);
+                    const double2 ww = *reinterpret_cast<const double2 *>(wv + 2 * j);
+                    v.x *= ww.x;
+                    v.y *= ww.y;
+                    *reinterpret_cast<double2 *>(dst + 2 * q) = v;
+                }
+                fence_proxy_async();      // these generic-proxy writes precede the TMA refill of the slot
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[s]);
+            }
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_MMA_REGS));
+    }
 
     const uint32_t stage_bytes = TILE_BYTES * (diag ? 1u : 2u) + (WEIGHTED ? BK * 8u : 0u);
     auto issue = [&](int kt) {
@@ -192,7 +234,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int rho = g2_rho(lane >> 2);
     const int rowA = (plan.wm * 32 + rho) * BK;
     const int rowB = (plan.wn * 32 + rho) * BK;
-    const double *b_base = (diag && !WSMEM) ? sA : sB;
+    const double *b_base = (diag && !WSMEM && !WSPEC) ? sA : sB;
 
     for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % STAGES;
@@ -202,7 +244,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty[sp], ((kt - 1) / STAGES) & 1);
             issue(kt - 1 + STAGES);
         }
-        mbar_wait(WSMEM ? &ready[s] : &full[s], (kt / STAGES) & 1);
+        mbar_wait((WSMEM || WSPEC) ? &ready[s] : &full[s], (kt / STAGES) & 1);
         const double *a_s = sA + s * TILE_ELEMS + rowA;
         const double *b_s = b_base + s * TILE_ELEMS + rowB;
         const double *w_s = sW + s * BK;
@@ -300,6 +342,10 @@ int pmc_gram2_launch(pmc_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tm
         PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)GRAM2_SMEM));
         gram2_dmma_kernel<1><<<(unsigned)items, THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
+    } else if (weighted && (p.opts & G2_OPT_W_WARPSPEC)) {
+        PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)GRAM2_SMEM));
+        gram2_dmma_kernel<4><<<(unsigned)items, WS_THREADS, GRAM2_SMEM, ctx->stream>>>(tmA, tmB, tmW, p);
     } else if (weighted && (p.opts & G2_OPT_W_NIMAJOR)) {
         PMC_CHECK_CUDA(cudaFuncSetAttribute(gram2_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)GRAM2_SMEM));
