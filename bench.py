@@ -68,9 +68,21 @@ if ARGS.impl == 'reference':
     if RANK != 0:                                     # under torchrun rank 0 alone runs the reference arm
         sys.exit(0)
     os.environ['OMP_NUM_THREADS'] = os.environ['OPENBLAS_NUM_THREADS'] = str(os.cpu_count() or 1)
-elif WORLD > 1 and os.environ.get('OMP_NUM_THREADS', '1') == '1':
-    _share = max(1, (os.cpu_count() or 1) // int(os.environ.get('LOCAL_WORLD_SIZE', WORLD)))
-    os.environ['OMP_NUM_THREADS'] = os.environ['OPENBLAS_NUM_THREADS'] = str(_share)
+elif WORLD > 1:
+    _local_world = int(os.environ.get('LOCAL_WORLD_SIZE', WORLD))
+    _share = max(1, (os.cpu_count() or 1) // _local_world)
+    if os.environ.get('OMP_NUM_THREADS', '1') == '1':
+        os.environ['OMP_NUM_THREADS'] = os.environ['OPENBLAS_NUM_THREADS'] = str(_share)
+    # ... and its own block of cores: N ranks x (LAPACK threads + NCCL / driver helper threads) migrating over one
+    # socket make the replicated eigensolves finish at different times, and the slowest rank sets the step time
+    try:
+        _cores = sorted(os.sched_getaffinity(0))
+        _lr = int(os.environ.get('LOCAL_RANK', '0'))
+        _per = len(_cores) // _local_world
+        if _per >= 1 and os.environ.get('PMC_BENCH_NO_PINNING', '0') != '1':
+            os.sched_setaffinity(0, _cores[_lr * _per:(_lr + 1) * _per])
+    except (AttributeError, OSError):
+        pass
 
 import numpy as np  # noqa: E402
 
@@ -82,6 +94,9 @@ METRIC = 'POD (pymor pod, method_of_snapshots, diag-W product) FP64 TFLOP/s, 10M
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel, from `ncu --set full` captures of this
 # very workload, keyed by (kernel, rows per GPU, k); see profiles/ for the reports.
 NCU_TRAFFIC = {
+    ('gram', 10_000_000, 1000): (238.067654e9 + 3.538929e9, 'profiles/r02_ncu_gram2_default_10Mx1000_dram.csv (one weighted SYRK launch; '
+                                 '80.08 GB of operands: the tiles of a row range are dispatched staggered and re-read '
+                                 'part of it from DRAM, DESIGN.md §3)'),
     ('lincomb', 10_000_000, 1000): (80.138563e9 + 79.989229e9, 'profiles/r01_ncu_full_lincomb_10Mx1000_details.txt'),
     ('lincomb', 2_000_000, 500): (8.006061e9 + 7.963813e9, 'profiles/r01b_ncu_full_details.txt'),
 }

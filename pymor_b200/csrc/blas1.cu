@@ -368,6 +368,7 @@ __device__ __forceinline__ bool amax_better(double v, int64_t i, double bv, int6
     return i < bi;
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(TPB)
 amax_kernel(const double *__restrict__ A, int64_t csA, int64_t n, double *__restrict__ pval,
             int64_t *__restrict__ pidx, unsigned int *__restrict__ tickets,
@@ -376,11 +377,25 @@ amax_kernel(const double *__restrict__ A, int64_t csA, int64_t n, double *__rest
     const double *a = A + (int64_t)c * csA;
     double bv = -1.0;
     int64_t bi = INT64_MAX;
+    // (amax_better is a total order on (value, index): the result does not depend on the order of the comparisons)
     for (int64_t base = (int64_t)blockIdx.x * CHUNK; base < n; base += (int64_t)bx * CHUNK) {
-        const int64_t end = (base + CHUNK < n) ? base + CHUNK : n;
-        for (int64_t i = base + threadIdx.x; i < end; i += TPB) {
-            const double v = fabs(a[i]);
-            if (amax_better(v, i, bv, bi)) { bv = v; bi = i; }
+        if (VEC && base + CHUNK <= n) {
+            double2 xv[UNROLL];                       // UNROLL independent 128-bit loads in flight
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) xv[u] = ld_stream2(a + base + 2 * (threadIdx.x + u * TPB));
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t i = base + 2 * (threadIdx.x + u * TPB);
+                const double v0 = fabs(xv[u].x), v1 = fabs(xv[u].y);
+                if (amax_better(v0, i, bv, bi)) { bv = v0; bi = i; }
+                if (amax_better(v1, i + 1, bv, bi)) { bv = v1; bi = i + 1; }
+            }
+        } else {
+            const int64_t end = (base + CHUNK < n) ? base + CHUNK : n;
+            for (int64_t i = base + threadIdx.x; i < end; i += TPB) {
+                const double v = fabs(a[i]);
+                if (amax_better(v, i, bv, bi)) { bv = v; bi = i; }
+            }
         }
     }
 #pragma unroll
@@ -561,8 +576,12 @@ extern "C" int pmc_amax(pmc_ctx *ctx, const double *A, int64_t csA, int32_t k, i
         int bx = blocks_per_col(ctx, n, kc, 8);
         while ((int64_t)bx * kc > cap && bx > 1) bx = (bx + 1) / 2;
         dim3 grid(bx, kc);
-        amax_kernel<<<grid, TPB, 0, ctx->stream>>>(A + (int64_t)c0 * csA, csA, n, pb, pi, ctx->tickets,
-                                                   out_idx + c0, out_val + c0);
+        if (vec_ok(A, csA))
+            amax_kernel<true><<<grid, TPB, 0, ctx->stream>>>(A + (int64_t)c0 * csA, csA, n, pb, pi, ctx->tickets,
+                                                             out_idx + c0, out_val + c0);
+        else
+            amax_kernel<false><<<grid, TPB, 0, ctx->stream>>>(A + (int64_t)c0 * csA, csA, n, pb, pi, ctx->tickets,
+                                                              out_idx + c0, out_val + c0);
         ++launches;
     }
     return pmc_after_launch(ctx, launches, flags);

@@ -714,6 +714,11 @@ class CudaVectorSpace(VectorSpace):
             return host[1][:count].copy()
         part = buf[:count]
         self._comm.allreduce_sum_(part)
+        if part.is_cuda:                                # D2H through the context's pinned buffer: one DMA, no staging
+            host = self._ctx.host_f64(count)[:count]
+            host.copy_(part, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return host.numpy().copy()
         return part.to('cpu').numpy().copy()
 
     # -- factory ------------------------------------------------------------------------------

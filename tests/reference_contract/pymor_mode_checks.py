@@ -137,11 +137,15 @@ def test_randomized_range_finder_next_row_N2():
         Qn = RandomizedRangeFinder(on, power_iterations=1).find_range(basis_size=8)
     with new_rng(3):
         Qc = RandomizedRangeFinder(oc, power_iterations=1).find_range(basis_size=8)
-    # the 5 dominant directions agree tightly; directions 6-8 are resolved out of the 1e-6 perturbation, i.e.
-    # conditioned like 1e6 * eps w.r.t. any change of rounding between the two backends
+    # the 5 dominant directions agree tightly; directions 6-8 are resolved out of the 1e-6 perturbation after one
+    # power iteration, i.e. out of components of relative size 1e-12: they are conditioned like 1e12 * eps w.r.t. any
+    # change of rounding between the two backends and are compared through what they are for -- the range they add
     np.testing.assert_allclose(Qc.to_numpy()[:, :5], Qn.to_numpy()[:, :5], atol=1e-9)
-    np.testing.assert_allclose(Qc.to_numpy(), Qn.to_numpy(), atol=1e-6)
     assert np.max(np.abs(Qc.gramian() - np.eye(8))) < 1e-12
+    Md0 = M.toarray()
+    res_c = np.linalg.norm(Md0 - Qc.to_numpy() @ (Qc.to_numpy().T @ Md0), 2)
+    res_n = np.linalg.norm(Md0 - Qn.to_numpy() @ (Qn.to_numpy().T @ Md0), 2)
+    assert res_c <= 1.01 * res_n + 1e-12 and res_c < 2e-6
     with new_rng(4):
         Un, sn, Vn = randomized_svd(on, 5)
     with new_rng(4):
@@ -160,7 +164,7 @@ def test_randomized_range_finder_next_row_N2():
             fc = RandomizedRangeFinder(oc, power_iterations=1, error_estimator=est, block_size=2)
             Bc = fc.find_range(tol=1e-3)
         assert len(Bc) == len(Bn) and 5 <= len(Bc) <= 12
-        np.testing.assert_allclose(fc.last_estimated_error, fn.last_estimated_error, rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(fc.last_estimated_error, fn.last_estimated_error, rtol=1e-3, atol=1e-12)
         Bh = Bc.to_numpy()
         assert np.linalg.norm(Md - Bh @ (Bh.T @ Md), 2) < 1e-3
         np.testing.assert_allclose(Bh[:, :5], Bn.to_numpy()[:, :5], atol=1e-9)
