@@ -48,6 +48,8 @@ def parse_args(argv):
     ap.add_argument('--c5', default='auto', choices=['auto', 'on', 'off'],
                     help="secondary block: BASELINE config 5, project() of a 5-point CSR operator onto 2000 basis vectors, "
                          "6.25M DOF per GPU (50M at 8 GPUs); auto = at 8 GPUs")
+    ap.add_argument('--no-gs', action='store_true',
+                    help='skip the secondary block "config 3: re-iterated Gram-Schmidt of 10M x 256 with a diagonal product"')
     ap.add_argument('--no-csr-pod', action='store_true',
                     help='N = 1: skip the secondary block "POD with a CSR (tridiagonal FEM mass matrix) product"')
     ap.add_argument('--accelerate', action='store_true',
@@ -489,33 +491,102 @@ def run_cuda(args):
             'secondary': {'pod_csr_product': csr_pod} if csr_pod else None, 'accelerated': accelerated, 'gpu_launches': int(launches), 'clocks': clocks,
         }
 
-    # ---- secondary: BASELINE config 5 (RB projection V^T A V, 50M DOF x 2000 basis at 8 GPUs) ---------------
-    # Runs last and under a watchdog: whatever happens here, the contract line above is printed exactly once.
-    if args.c5 == 'on' or (args.c5 == 'auto' and world == 8):
+    # ---- secondary blocks: BASELINE config 3 (re-iterated Gram-Schmidt, 10M x 256) at every N and config 5 (RB
+    # projection V^T A V, 50M DOF x 2000 basis) at 8 GPUs.  They run last and under a watchdog: whatever happens
+    # here, the contract line above is printed exactly once.
+    want_c5 = args.c5 == 'on' or (args.c5 == 'auto' and world == 8)
+    if want_c5 or not args.no_gs:
+        extra = {}
+
         def give_up():
             if rank == 0:
-                line['secondary'] = {'projection_c5': {'error': 'timed out after 300 s'}}
+                extra['error'] = 'secondary blocks timed out after 400 s'
+                line['secondary'] = dict(line['secondary'] or {}, **extra)
                 print(json.dumps(line), flush=True)
             os._exit(0)
-        watchdog = threading.Timer(300.0, give_up)
+        watchdog = threading.Timer(400.0, give_up)
         watchdog.daemon = True
         watchdog.start()
-        try:
-            sys.path.insert(0, str(ROOT / 'tools'))
-            from bench_project import run_projection
-            nx, ny = 5000, 1250 * world                    # 6.25M DOF per GPU; the shard boundary is one grid line
-            pspace = CudaVectorSpace(nx * ny, device=device, comm=comm)
-            barrier()
-            result = run_projection(pspace, nx, ny, 2000, reps=2, comm=comm)
-        except Exception as exc:
-            result = {'error': f'{type(exc).__name__}: {exc}'}
+        torch.cuda.empty_cache()
+        if not args.no_gs:
+            try:
+                extra['gram_schmidt_c3'] = gram_schmidt_c3(device, comm, barrier)
+            except Exception as exc:
+                extra['gram_schmidt_c3'] = {'error': f'{type(exc).__name__}: {exc}'}
+            torch.cuda.empty_cache()
+        if want_c5:
+            try:
+                sys.path.insert(0, str(ROOT / 'tools'))
+                from bench_project import run_projection
+                nx, ny = 5000, 1250 * world                # 6.25M DOF per GPU; the shard boundary is one grid line
+                pspace = CudaVectorSpace(nx * ny, device=device, comm=comm)
+                barrier()
+                extra['projection_c5'] = run_projection(pspace, nx, ny, 2000, reps=2, comm=comm)
+            except Exception as exc:
+                extra['projection_c5'] = {'error': f'{type(exc).__name__}: {exc}'}
         watchdog.cancel()
         if rank == 0:
-            line['secondary'] = dict(line['secondary'] or {}, projection_c5=result)
+            line['secondary'] = dict(line['secondary'] or {}, **extra)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gram_schmidt_c3(device, comm, barrier, n=10_000_000, k=256):
+    """BASELINE config 3: re-iterated Gram-Schmidt of k vectors with a diagonal mass-matrix product, rows sharded
+    over the ranks.  Input family of SURVEY.md §8d (a_i = g_i + 2 s: every vector re-iterates exactly once, k(k-1)
+    pair-steps).  pyMOR's own `gram_schmidt` (one host-synchronised dot + axpy per pair: gram_schmidt.py:84-91) next to
+    the device-friendly formulations of the same factorisation: `sweep=True` (one fused kernel per pass, sums over
+    the GPUs inside the kernel), `variant='bcgs2'` (panels on the tensor cores) and pyMOR's `shifted_chol_qr`.  Every
+    result is checked: orthonormality, A = Q R, and R against pyMOR's R."""
+    import torch
+    from pymor.algorithms.chol_qr import shifted_chol_qr
+    from pymor.algorithms.gram_schmidt import gram_schmidt
+
+    from pymor_b200 import algorithms as alg
+    from pymor_b200.operators import CudaDiagonalOperator
+    from pymor_b200.vectorarray import CudaVectorSpace
+    rank = comm.rank if comm is not None else 0
+    space = CudaVectorSpace(n, device=device, comm=comm)
+    A0 = space.random_device(k, seed=1, scale=1.0 / np.sqrt(n))
+    A0.axpy(2.0, space.random_device(1, seed=2, scale=1.0 / np.sqrt(n)))
+    gen = torch.Generator(device=device).manual_seed(3 + rank)
+    w = torch.rand(space.local_dim, generator=gen, device=device, dtype=torch.float64) + 0.5
+    prod = CudaDiagonalOperator(w, space)
+    variants = [
+        ('pymor_gram_schmidt', lambda A: gram_schmidt(A, product=prod, return_R=True, check=False, copy=False)),
+        ('sweep', lambda A: alg.gram_schmidt(A, product=prod, return_R=True, check=False, copy=False, sweep=True)),
+        ('bcgs2', lambda A: alg.gram_schmidt(A, product=prod, return_R=True, check=False, copy=False, variant='bcgs2')),
+        ('pymor_shifted_chol_qr', lambda A: shifted_chol_qr(A, product=prod, return_R=True, copy=False,
+                                                            product_norm=float(np.sqrt(1.5)))),
+    ]
+    out, R_ref = {}, None
+    anorm = float(np.max(A0.norm(prod)))
+    for name, fn in variants:
+        fn(A0[:8].copy())                                       # warm the kernels / the code path
+        A = A0.copy(deep=True)
+        barrier()
+        t0 = time.perf_counter()
+        Q, R = fn(A)
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        if comm is not None:
+            dt = max(comm.allgather_object(dt))
+        D = Q.lincomb(R)
+        D.axpy(-1.0, A0)
+        res = {'seconds': dt, 'orth_err_max_abs(Q^T W Q - I)': float(np.max(np.abs(Q.gramian(prod) - np.eye(len(Q))))),
+               'reconstruction_rel_err(A - Q R)': float(np.max(D.norm(prod)) / anorm), 'len_Q': len(Q)}
+        if name == 'pymor_gram_schmidt':
+            R_ref = R
+            res['us_per_pair_step'] = dt / (k * (k - 1)) * 1e6
+        elif R_ref is not None and R.shape == R_ref.shape:
+            res['R_vs_pymor_gram_schmidt_rel'] = float(np.max(np.abs(R - R_ref)) / np.max(np.abs(R_ref)))
+        out[name] = res
+        del Q, D, A
+    out['workload'] = (f'orthonormalisation of {n} x {k}, diagonal product, a_i = g_i + 2 s (every vector re-iterates once: '
+                       f'{k * (k - 1)} pair-steps in modified Gram-Schmidt), rows sharded over {comm.size if comm else 1} GPU(s)')
+    return out
 
 
 def csr_weighted_pod(args, make_problem, timed_loop, pod_step):
