@@ -554,28 +554,35 @@ def gram_schmidt_c3(device, comm, barrier, n=10_000_000, k=256):
     gen = torch.Generator(device=device).manual_seed(3 + rank)
     w = torch.rand(space.local_dim, generator=gen, device=device, dtype=torch.float64) + 0.5
     prod = CudaDiagonalOperator(w, space)
+    # (name, function, runs): the variants that allocate full-size temporaries (block lincombs) are run more than
+    # once and the best run is reported -- their first call pays for the caching allocator's fresh 20 GB mappings
     variants = [
-        ('pymor_gram_schmidt', lambda A: gram_schmidt(A, product=prod, return_R=True, check=False, copy=False)),
-        ('sweep', lambda A: alg.gram_schmidt(A, product=prod, return_R=True, check=False, copy=False, sweep=True)),
-        ('bcgs2', lambda A: alg.gram_schmidt(A, product=prod, return_R=True, check=False, copy=False, variant='bcgs2')),
+        ('pymor_gram_schmidt', lambda A: gram_schmidt(A, product=prod, return_R=True, check=False, copy=False), 1),
+        ('sweep', lambda A: alg.gram_schmidt(A, product=prod, return_R=True, check=False, copy=False, sweep=True), 1),
+        ('bcgs2', lambda A: alg.gram_schmidt(A, product=prod, return_R=True, check=False, copy=False, variant='bcgs2'), 2),
         ('pymor_shifted_chol_qr', lambda A: shifted_chol_qr(A, product=prod, return_R=True, copy=False,
-                                                            product_norm=float(np.sqrt(1.5)))),
+                                                            product_norm=float(np.sqrt(1.5))), 3),
     ]
     out, R_ref = {}, None
     anorm = float(np.max(A0.norm(prod)))
-    for name, fn in variants:
+    for name, fn, runs in variants:
         fn(A0[:8].copy())                                       # warm the kernels / the code path
-        A = A0.copy(deep=True)
-        barrier()
-        t0 = time.perf_counter()
-        Q, R = fn(A)
-        torch.cuda.synchronize(device)
-        dt = time.perf_counter() - t0
-        if comm is not None:
-            dt = max(comm.allgather_object(dt))
+        all_dt = []
+        for _ in range(runs):
+            Q = R = None
+            A = A0.copy(deep=True)
+            barrier()
+            t0 = time.perf_counter()
+            Q, R = fn(A)
+            torch.cuda.synchronize(device)
+            dt = time.perf_counter() - t0
+            if comm is not None:
+                dt = max(comm.allgather_object(dt))
+            all_dt.append(dt)
+        dt = min(all_dt)
         D = Q.lincomb(R)
         D.axpy(-1.0, A0)
-        res = {'seconds': dt, 'orth_err_max_abs(Q^T W Q - I)': float(np.max(np.abs(Q.gramian(prod) - np.eye(len(Q))))),
+        res = {'seconds': dt, 'all_seconds': all_dt, 'orth_err_max_abs(Q^T W Q - I)': float(np.max(np.abs(Q.gramian(prod) - np.eye(len(Q))))),
                'reconstruction_rel_err(A - Q R)': float(np.max(D.norm(prod)) / anorm), 'len_Q': len(Q)}
         if name == 'pymor_gram_schmidt':
             R_ref = R
