@@ -252,6 +252,15 @@ class CudaCsrOperator(Operator):
         object.__setattr__(op, '_dev', _ShardedCsr(local_rows, space, rows_are_local=True))
         return op
 
+    def with_(self, **kwargs):
+        """pyMOR's copy-with-changes (``ImmutableObject.with_`` re-runs ``__init__``): operators built from per-rank
+        rows or device CSR arrays have no host matrix to rebuild from, so their device block is carried over."""
+        new = super().with_(**kwargs)
+        if new._dev is None and self._dev is not None and new.space == self.space:
+            object.__setattr__(new, '_dev', self._dev)
+            object.__setattr__(new, '_dev_T', self._dev_T)
+        return new
+
     def is_symmetric(self):
         """Whether the matrix is symmetric: the ``symmetric`` argument, else a host check cached on first use
         (``False`` without a host matrix)."""

@@ -221,6 +221,10 @@ def test_csr_operator_symmetric_lower_only_and_local_rows(emu, rng):
     np.testing.assert_allclose(VA[:9].norm(loc), O.norm(A[:, :9], P), atol=1e-13)
     X = loc.apply_inverse(loc.apply(VA[:3]))        # symmetric => device CG with the Jacobi preconditioner
     np.testing.assert_allclose(X.to_numpy(), A[:, :3], atol=1e-7)
+    from pymor_b200.solvers import CgSolver
+    loc2 = loc.with_(solver=CgSolver(tol=1e-12), name='again')      # ImmutableObject.with_ re-runs __init__
+    assert loc2.name == 'again' and loc2.is_symmetric()
+    np.testing.assert_allclose(loc2.apply(VA[:2]).to_numpy(), P @ A[:, :2], atol=1e-14)
     nonsym = CudaCsrOperator.from_local_rows(N[sp.offset:sp.offset + sp.local_dim], sp)
     with pytest.raises(NotImplementedError):
         nonsym.apply_adjoint(VA[:2])
