@@ -241,6 +241,10 @@ int pmc_comm_init(pmc_ctx *ctx, int rank, int size, const void *id_bytes);
 int pmc_comm_destroy(pmc_ctx *ctx);
 int pmc_comm_size(pmc_ctx *ctx); /* 0 without a communicator */
 int pmc_allreduce_sum(pmc_ctx *ctx, double *buf, int64_t count, uint32_t flags);
+/* G[j + i*ld] = G[i + j*ld] for i > j (device memory, column-major k x k): restores the bitwise symmetry of a
+ * Gramian after the cross-GPU sum, whose chunks are added in different rank orders (the reference's syrk result and
+ * its rank-ordered host sum are symmetric: vectorarrays/numpy.py:155-163, mpi.py:394-416). */
+int pmc_mirror_lower(pmc_ctx *ctx, double *G, int64_t k, int64_t ld, uint32_t flags);
 
 /* Roofline denominators measured on the spot: sustained FP64 tensor-core (DMMA) and DFMA
  * throughput in TFLOP/s over `ms` milliseconds of back-to-back issue on every SM.  use_dmma: 0 = DFMA, 1 = DMMA,

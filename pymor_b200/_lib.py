@@ -57,6 +57,7 @@ _CTX_FUNCS = {
     'pmc_comm_init': [c_int, c_int, _P],
     'pmc_comm_destroy': [],
     'pmc_allreduce_sum': [_P, _I64, _U32],
+    'pmc_mirror_lower': [_P, _I64, _I64, _U32],
     'pmc_ctx_set_option': [ctypes.c_char_p, c_int],
     'pmc_ctx_get_option': [ctypes.c_char_p, ctypes.POINTER(c_int)],
     'pmc_ctx_kernel_times': [_P, _P, _I32, ctypes.POINTER(_I32)],

@@ -352,6 +352,16 @@ shift_cols_kernel(double *__restrict__ A, int64_t cs, int64_t first, int64_t cou
     }
 }
 
+// After a cross-GPU all-reduce the two halves of a symmetric k x k result may differ in the last bit (the
+// collective sums different chunks in different rank orders): copy the lower triangle over the upper one so that
+// the Gramian stays bitwise symmetric, like the reference's syrk result.
+__global__ void mirror_lower_kernel(double *__restrict__ G, int64_t k, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= k * k) return;
+    const int64_t i = e % k, j = e / k;
+    if (i > j) G[j + i * ld] = G[i + j * ld];
+}
+
 __global__ void dofs_kernel(const double *__restrict__ A, int64_t csA, int k, IndexPack dof, int nd,
                             int ndofs_total, int dof0, double *__restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -528,6 +538,14 @@ extern "C" int pmc_gather_cols(pmc_ctx *ctx, double *D, int64_t csD, const doubl
         ++launches;
     }
     return pmc_after_launch(ctx, launches, flags);
+}
+
+extern "C" int pmc_mirror_lower(pmc_ctx *ctx, double *G, int64_t k, int64_t ld, uint32_t flags) {
+    PMC_REQUIRE(ctx && k >= 0 && ld >= k, "bad arguments");
+    if (k <= 1) return pmc_after_launch(ctx, 0, flags);
+    PMC_REQUIRE(G != nullptr, "G is NULL");
+    mirror_lower_kernel<<<(unsigned)ceil_div64(k * k, 256), 256, 0, ctx->stream>>>(G, k, ld);
+    return pmc_after_launch(ctx, 1, flags);
 }
 
 extern "C" int pmc_shift_cols(pmc_ctx *ctx, double *A, int64_t cs, int64_t first, int64_t count, int64_t shift,

@@ -80,6 +80,35 @@ __device__ __forceinline__ void stage_mma(double (&acc)[4][4][2], const double *
     }
 }
 
+// Full general tiles with a register-scaled weight: 64 x 16 warp tiles (warp = (wm2, wn2) of a 2 x 8 grid) instead of
+// 32 x 32.  Same 16 DMMA per quarter-step and the same 32 accumulators, but only TWO B fragments to scale (2 DMUL
+// instead of 4: the weight costs half the FP64-pipe time and half the DMUL -> DMMA dependencies) for two more fragment
+// loads.  Sub-block (m8, ni), m8 = 4 h + mi, lives in acc[mi][2 h + ni]; every accumulator receives the same
+// products in the same order as in the 32 x 32 layout, so the result is bitwise the same.
+__device__ __forceinline__ void stage_mma_wide(double (&acc)[4][4][2], const double *a_s, const double *b_s,
+                                               const int (&fo)[4], const double *w_s, const int (&wo)[4]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        double b[2];
+        b[0] = b_s[fo[ks]];
+        b[1] = b_s[8 * BK + fo[ks]];
+        const double wv = w_s[wo[ks]];
+        b[0] *= wv;
+        b[1] *= wv;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double a[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = a_s[(h * 4 + mi) * 8 * BK + fo[ks]];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni)
+                    dmma884(acc[mi][h * 2 + ni][0], acc[mi][h * 2 + ni][1], a[mi], b[ni]);
+        }
+    }
+}
+
 // shape codes of the warp-uniform dispatch in the stage loop: rectangular blocks (nm-1)*4 + (nn-1), + 16 when the
 // warp contracts half of the stage (2 quarter-steps), + 32 for a quarter; triangular (diagonal) blocks 48 + nm-1
 constexpr int SHAPE_IDLE = -1, SHAPE_TRI = 48;
@@ -235,6 +264,15 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int rowA = (plan.wm * 32 + rho) * BK;
     const int rowB = (plan.wn * 32 + rho) * BK;
     const double *b_base = (diag && !WSMEM && !WSPEC) ? sA : sB;
+    // full general tile, weight scaled in registers: 64 x 16 warp tiles (CTA-uniform choice)
+    const bool wide = WREG != 0 && !diag && vm == BM && vn == BN && !(p.opts & G2_OPT_NO_WIDE);
+    const int wide_rowA = ((warp & 1) * 64 + rho) * BK, wide_rowB = ((warp >> 1) * 16 + rho) * BK;
+    int fo0[4], wo0[4];                             // fragment / weight offsets of the full K range (ks0 = 0)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        fo0[i] = g2_frag_offset(i, lane);
+        wo0[i] = i * 4 + (lane & 3);
+    }
 
     for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % STAGES;
@@ -248,6 +286,9 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const double *a_s = sA + s * TILE_ELEMS + rowA;
         const double *b_s = b_base + s * TILE_ELEMS + rowB;
         const double *w_s = sW + s * BK;
+        if (WREG != 0 && wide) {
+            stage_mma_wide(acc, sA + s * TILE_ELEMS + wide_rowA, sB + s * TILE_ELEMS + wide_rowB, fo0, w_s, wo0);
+        } else
         switch (shape) {
 #define G2_RECT(NM, NN)                                                                                   \
     case (NM - 1) * 4 + (NN - 1): stage_mma<NM, NN, false, 4, WREG>(acc, a_s, b_s, fo, w_s, wo); break;                  \
@@ -270,7 +311,20 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 
     // epilogue: partial tile, column-major [j][i]; sub-blocks nobody reads later are not written
-    if (plan.active) {
+    if (WREG != 0 && wide) {
+        double *out = p.partials + (size_t)item * (BM * BN);
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int h = q >> 1, ni = q & 1;
+                const int i = (warp & 1) * 64 + (h * 4 + mi) * 8 + g2_rho(g);
+                const int j = (warp >> 1) * 16 + ni * 8;
+                out[(size_t)(j + g2_rho(2 * t)) * BM + i] = acc[mi][q][0];
+                out[(size_t)(j + g2_rho(2 * t + 1)) * BM + i] = acc[mi][q][1];
+            }
+    } else if (plan.active) {
         double *out = p.partials + (size_t)item * (BM * BN);
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)

@@ -333,6 +333,8 @@ class CudaCsrOperator(Operator):
                         ghost.data_ptr() if ghost is not None else 0, out.data_ptr(), kv, flags)
         if sp.comm.size > 1:
             sp.comm.allreduce_sum_(out)
+            if (flags & PMC_LOWER_ONLY) and sp.comm.size > 2:    # the collective may break the mirrored halves' equality
+                sp.ctx.call('pmc_mirror_lower', out.data_ptr(), kv, kv, 0)
         del keep_v, keep_u
         return out.to('cpu').numpy().reshape((kv, ku), order='F')
 

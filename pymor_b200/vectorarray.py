@@ -424,7 +424,7 @@ class CudaVectorArrayImpl(VectorArrayImpl):
         sp.ctx.call('pmc_gram', pa, csa, ka, pb, csb, kb, self.n, weight_ptr, out.data_ptr(), ka,
                     flags | sp.kernel_flags)
         del keep_a, keep_b
-        return sp.reduction_result(out, ka * kb).reshape((ka, kb), order='F')
+        return sp.reduction_result(out, ka * kb, symmetric_k=ka if symmetric else 0).reshape((ka, kb), order='F')
 
     def gramian(self, ind):
         return self.inner(self, ind, ind)
@@ -704,7 +704,10 @@ class CudaVectorSpace(VectorSpace):
             self._red_dev = torch.empty(max(int(count), 4096), dtype=torch.float64, device=self.device)
         return self._red_dev, 0
 
-    def reduction_result(self, buf, count):
+    def reduction_result(self, buf, count, symmetric_k=0):
+        """Host copy of ``count`` reduced doubles (summed over the ranks).  ``symmetric_k``: the result is a symmetric
+        ``k x k`` matrix -- after a cross-GPU all-reduce its lower triangle is mirrored (``pmc_mirror_lower``), because
+        the collective adds different chunks in different rank orders."""
         if type(buf) is _RawTarget:
             return self._host_reducer.finish(count)
         if self._comm.size == 1:
@@ -714,6 +717,8 @@ class CudaVectorSpace(VectorSpace):
             return host[1][:count].copy()
         part = buf[:count]
         self._comm.allreduce_sum_(part)
+        if symmetric_k > 1 and self._comm.size > 2:
+            self._ctx.call('pmc_mirror_lower', part.data_ptr(), symmetric_k, symmetric_k, 0)
         if part.is_cuda:                                # D2H through the context's pinned buffer: one DMA, no staging
             host = self._ctx.host_f64(count)[:count]
             host.copy_(part, non_blocking=True)

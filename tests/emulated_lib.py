@@ -255,6 +255,13 @@ class EmulatedLib:
             _col(Y, csY, c, nrows)[:] = y[:, c]
         return PMC_OK
 
+    def pmc_mirror_lower(self, ctx, G, k, ld, flags):
+        self._note('pmc_mirror_lower')
+        g = _vec(G, ld * k).reshape((ld, k), order='F')
+        low = np.tril_indices(k, -1)
+        g[low[1], low[0]] = g[low]
+        return PMC_OK
+
     def pmc_shift_cols(self, ctx, A, cs, first, count, shift, n, flags):
         self._note('pmc_shift_cols')
         for c in range(first, first + count):                 # increasing order: overlapping ranges are fine

@@ -67,7 +67,16 @@ def main():
         np.testing.assert_allclose(G, O.inner(A, B), atol=1e-12)
         parts = [O.inner(A[o:o + d], B[o:o + d]) for o, d in zip(offs, dims)]
         np.testing.assert_allclose(G, O.sharded_reduce(parts), atol=1e-12)
-        np.testing.assert_allclose(VA.gramian(prod), O.gramian(A, w), atol=1e-12)
+        Gs = VA.gramian(prod)
+        np.testing.assert_allclose(Gs, O.gramian(A, w), atol=1e-12)
+        np.testing.assert_array_equal(Gs, Gs.T)      # bitwise symmetric also after the cross-rank sum
+        if dim >= 103:
+            # more than 2048 entries: the partials are summed by the all-reduce on the device (not by the host
+            # reducer), whose chunks are added in different rank orders -- the lower triangle is mirrored afterwards
+            W64 = rng.standard_normal((dim, 64))
+            G64 = sp.from_numpy(W64).gramian(prod)
+            np.testing.assert_allclose(G64, O.gramian(W64, w), atol=1e-11)
+            np.testing.assert_array_equal(G64, G64.T)
         np.testing.assert_allclose(VA.pairwise_inner(VB, prod), O.pairwise_inner(A, B, w), atol=1e-12)
         np.testing.assert_allclose(VA.norm(), O.norm(A), atol=1e-12)
         np.testing.assert_allclose(VA[2:7].norm2(prod), O.norm2(A[:, 2:7], w), atol=1e-12)

@@ -97,7 +97,7 @@ def _block_error_map(G, G_ref, scale):
 
 
 @pytest.mark.parametrize('opts', [16, 16 | 32, 16 | 64, 16 | 128, 16 | 32 | 64 | 128, 16 | 256, 16 | 64 | 256, 16 | 512,
-                                  16 | 64 | 512, 16 | 1024, 16 | 64 | 1024])
+                                  16 | 64 | 512, 16 | 1024, 16 | 64 | 1024, 16 | 2048, 16 | 64 | 2048])
 def test_gram2_variant_parity(loaded_lib, rng, opts):
     from pymor_b200._lib import get_context
     from pymor_b200.operators import CudaDiagonalOperator
