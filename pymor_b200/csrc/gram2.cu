@@ -147,13 +147,17 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tile = item % p.ntiles, split = item / p.ntiles;
     int ti, tj;
     decode_tile(p, tile, ti, tj);
-    const bool diag = p.symmetric == 1 && ti == tj;   // (symmetric == 2: lower tiles of a general product, two operands)
+    // Tiles on the diagonal of a symmetric result need their lower part only (`tri_tile`: the triangular warp plan);
+    // in a SYRK (symmetric == 1) the A tile serves both sides (`diag`: one operand is loaded), in the lower-only mode
+    // of a general product (symmetric == 2: V^T (M V) with symmetric M) the two operands differ.
+    const bool tri_tile = p.symmetric != 0 && ti == tj && !(p.opts & G2_OPT_NO_TRI2);
+    const bool diag = p.symmetric == 1 && ti == tj;
     const int64_t r0 = (int64_t)split * p.rows_per_split;
     const int64_t r1 = (r0 + p.rows_per_split < p.n) ? r0 + p.rows_per_split : p.n;
     const int nk = (r1 > r0) ? (int)((r1 - r0 + BK - 1) / BK) : 0;
 
     const int vm = min(BM, p.kA - ti * BM), vn = min(BN, p.kB - tj * BN);   // valid rows / cols of this tile
-    const G2Plan plan = g2_plan(warp < G2_WARPS ? warp : 0, diag, vm, vn, p.opts);
+    const G2Plan plan = g2_plan(warp < G2_WARPS ? warp : 0, diag || tri_tile, vm, vn, p.opts);
     const int shape = !plan.active ? SHAPE_IDLE
                       : plan.tri   ? SHAPE_TRI + plan.nm - 1
                                    : (plan.nm - 1) * 4 + (plan.nn - 1) + (plan.nks == 4 ? 0 : plan.nks == 2 ? 16 : 32);
@@ -265,7 +269,7 @@ gram2_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int rowB = (plan.wn * 32 + rho) * BK;
     const double *b_base = (diag && !WSMEM && !WSPEC) ? sA : sB;
     // full general tile, weight scaled in registers: 64 x 16 warp tiles (CTA-uniform choice)
-    const bool wide = WREG != 0 && !diag && vm == BM && vn == BN && !(p.opts & G2_OPT_NO_WIDE);
+    const bool wide = WREG != 0 && !diag && !tri_tile && vm == BM && vn == BN && !(p.opts & G2_OPT_NO_WIDE);
     const int wide_rowA = ((warp & 1) * 64 + rho) * BK, wide_rowB = ((warp >> 1) * 16 + rho) * BK;
     int fo0[4], wo0[4];                             // fragment / weight offsets of the full K range (ks0 = 0)
 #pragma unroll
@@ -349,7 +353,9 @@ __global__ void gram2_reduce_kernel(const double *__restrict__ partials, int nsp
     const int il = e % BM, jl = e / BM;
     const int gi = ti * BM + il, gj = tj * BN + jl;
     if (gi >= p.kA || gj >= p.kB) return;
-    const bool diag = p.symmetric == 1 && ti == tj;
+    // (same rule as in the tile kernel: the triangular plan -- and its slot layout -- on every diagonal tile of a
+    // symmetric result)
+    const bool diag = p.symmetric != 0 && ti == tj && (p.symmetric == 1 || !(p.opts & G2_OPT_NO_TRI2));
     if (p.symmetric && ti == tj && gi < gj) return; // strictly-upper part of diagonal tiles: mirrored
     const size_t tile_elems = (size_t)BM * BN;
     const double *src = partials + (size_t)tile * tile_elems;

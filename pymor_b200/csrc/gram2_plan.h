@@ -21,6 +21,7 @@ constexpr int G2_OPT_ENABLE = 16;      // use gram2_dmma_kernel instead of gram_
 constexpr int G2_OPT_NO_TRI = 32;      // diagonal blocks of diagonal SYRK tiles: all 16 sub-blocks
 constexpr int G2_OPT_NO_KSPLIT = 64;   // no K-split of two off-diagonal blocks of diagonal tiles
 constexpr int G2_OPT_NO_RAGGED = 128;  // partially filled blocks run in full
+constexpr int G2_OPT_NO_TRI2 = 4096;    // lower-only general product: diagonal tiles run in full instead of on the triangular plan (A/B)
 constexpr int G2_OPT_NO_WIDE = 2048;    // register-scaled weight: no 64x16 warp tiles on full general tiles (A/B)
 constexpr int G2_OPT_W_WARPSPEC = 1024; // weight applied in shared memory by a dedicated scaler warpgroup (warp specialisation, setmaxnreg)
 constexpr int G2_OPT_W_NIMAJOR = 512;  // register-scaled weight: stage weights loaded up front, ni-major DMMA order (A/B)
