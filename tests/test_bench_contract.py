@@ -84,3 +84,42 @@ def test_ctypes_tables_match_the_header():
         else:
             have = [ckind(t) for t in _lib._OTHER_FUNCS[name][0]]
         assert have == want, (name, have, want)
+
+
+def test_parity_block_logic_on_the_emulated_abi():
+    """bench.py's `parity` block (row sample against the unmodified reference on the same bits + size-independent
+    properties) on the NumPy-emulated C ABI: the block itself must report agreement to rounding."""
+    import argparse
+
+    import numpy as np
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / 'tests'))
+    from emulated_lib import EmulatedLib
+
+    from pymor_b200 import _lib
+    _lib.set_library_for_testing(EmulatedLib())
+    try:
+        import bench
+        import torch
+        from pymor.algorithms.pod import pod
+
+        from pymor_b200.operators import CudaDiagonalOperator
+        from pymor_b200.vectorarray import CudaVectorSpace
+        bench.quiet_pymor()
+        n, k = 30000, 40
+        rng = np.random.default_rng(1)
+        Qk, _ = np.linalg.qr(rng.standard_normal((k, k)))
+        A = (rng.standard_normal((n, k)) / np.sqrt(n)) @ (np.diag(bench.spectrum(k)) @ Qk.T)
+        space = CudaVectorSpace(n, device='cpu')
+        VA = space.from_numpy(A)
+        w = torch.from_numpy(rng.uniform(0.5, 1.5, n))
+        prod = CudaDiagonalOperator(w, space)
+        out = bench.parity_block(argparse.Namespace(k=k), space, VA, w, prod, None, 'cpu',
+                                 lambda arr, pr, **kw: pod(arr, product=pr, method='method_of_snapshots', **kw))
+    finally:
+        _lib.set_library_for_testing(None)
+    smp, full = out['sample'], out['full_size']
+    assert smp['ok'] and smp['rows'] == 20000 and smp['modes_kept'] == [k, k]
+    assert smp['singular_values_max_rel_err'] < 1e-12 and smp['subspace_angle_rad'] < 1e-10
+    assert full['orth_err_max_abs(U^T W U - I)'] < 1e-11 and full['gram_bitwise_symmetric']
+    assert full['trace_identity_rel_err(sum s^2 vs sum ||a_j||_W^2)'] < 1e-13 and full['singular_values_sorted']
