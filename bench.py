@@ -407,7 +407,10 @@ def run_cuda(args):
     # ---- parity (outside the timed region) -----------------------------------------------------------------
     parity = None
     if not args.no_parity:
-        parity = parity_block(args, space, A, w, prod, comm, device, pod_step)
+        try:
+            parity = parity_block(args, space, A, w, prod, comm, device, pod_step)
+        except Exception as exc:                          # never lose the contract line to the checker
+            parity = {'error': f'{type(exc).__name__}: {exc}'}
 
     # ---- optional: the same call with accelerate_pymor() active ------------------------------------------
     accelerated = None
