@@ -588,3 +588,37 @@ def test_accelerate_pymor_routes_device_arrays_to_block_gram_schmidt():
         restore_pymor()
         alg.block_gram_schmidt = real_bgs
     assert svd_mod.gram_schmidt is original and gs_mod.gram_schmidt is original
+
+
+def test_accelerate_pymor_selects_the_divide_and_conquer_eigensolver():
+    """`accelerate_pymor(eigh_driver='evd')`: the full eigensolve of `method_of_snapshots` (svd_va.py:82) runs with
+    LAPACK's divide-and-conquer driver, a call for a subset (modes given) keeps pyMOR's choice, the results agree
+    with the unpatched run, and `restore_pymor()` puts scipy.linalg back."""
+    import scipy.linalg as spla
+    import pymor.algorithms.svd_va as svd_mod
+
+    from pymor_b200.accelerate import accelerate_pymor, restore_pymor
+    A, nsp, csp, nprod, cprod = make(211, 14, 3, 'diag')
+    U0, s0, _ = method_of_snapshots(csp.from_numpy(A), product=cprod)
+    U0m, s0m, _ = method_of_snapshots(csp.from_numpy(A), product=cprod, modes=5)
+    seen = []
+    real = spla.eigh
+
+    def spy(a, *args, **kw):
+        seen.append((kw.get('driver'), kw.get('subset_by_index')))
+        return real(a, *args, **kw)
+    spla.eigh = spy
+    try:
+        accelerate_pymor(eigh_driver='evd')
+        assert svd_mod.spla is not spla
+        U1, s1, _ = svd_mod.method_of_snapshots(csp.from_numpy(A), product=cprod)
+        U1m, s1m, _ = svd_mod.method_of_snapshots(csp.from_numpy(A), product=cprod, modes=5)
+    finally:
+        restore_pymor()
+        spla.eigh = real
+    assert svd_mod.spla is spla
+    assert seen[0] == ('evd', None) and seen[1][0] is None and seen[1][1] is not None
+    np.testing.assert_allclose(s1, s0, rtol=1e-12)
+    np.testing.assert_allclose(s1m, s0m, rtol=1e-12)
+    G = U1.inner(U0, cprod)
+    np.testing.assert_allclose(np.abs(np.diag(G)), 1.0, atol=1e-9)
